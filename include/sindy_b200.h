@@ -1,0 +1,163 @@
+/*
+ * sindy_b200.h — C ABI of libsindy_b200.so: the B200 (sm_100a) implementation of the SINDy-family
+ * hot path of Rose-STL-Lab/symmetry-ode-discovery.
+ *
+ * The reference is pure Python/PyTorch and has no FFI of its own; every entry point below
+ * replaces the tensor arithmetic of one reference function (cited as file:line relative to the
+ * reference root). The host side that binds these symbols is
+ * `symmetry-ode-discovery_b200/sindy_b200/native.py` (ctypes); `INTEGRATION.md` shows the stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *  - every data pointer is a DEVICE pointer on the current CUDA device, row-major, contiguous;
+ *  - `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default stream); every call is
+ *    asynchronous on that stream and never synchronises the device;
+ *  - the caller owns all buffers, including workspaces (`sb_workspace_bytes`); nothing is retained
+ *    after the call returns except per-device constant tables;
+ *  - return value: 0 = ok, negative = `sb_status`; `sb_last_error()` gives a thread-local message;
+ *  - no C++ exception crosses the ABI; there is NO CPU fallback: without a CUDA device every
+ *    compute entry point returns SB_ERR_CUDA.
+ *
+ * Library column order (reference `sindy.py:7-30,68-77`): 1; x_0..x_{d-1}; then for n = 2..poly_order
+ * the degree-n monomials over non-decreasing index tuples in lexicographic order, each formed
+ * left to right ((x_i*x_j)*x_k...); then sin(x_i) (if include_sine); then exp(x_i) (if include_exp).
+ * The reference stops at degree 3 (`sindy.py:37`); degrees 4 and 5 continue the same enumeration.
+ */
+#ifndef SINDY_B200_H
+#define SINDY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SB_MAX_DIM 8
+#define SB_MAX_POLY 5
+#define SB_MAX_TERMS 256
+
+typedef enum {
+  SB_OK = 0,
+  SB_ERR_INVALID = -1,     /* bad argument (NULL pointer, negative size, misaligned buffer ...) */
+  SB_ERR_UNSUPPORTED = -2, /* library outside the supported range (dim, poly_order, K) */
+  SB_ERR_CUDA = -3,        /* CUDA runtime error (message in sb_last_error) */
+  SB_ERR_WORKSPACE = -4    /* workspace too small */
+} sb_status;
+
+/* Function library Θ: mirrors SINDyRegression(latent_dim, poly_order, include_sine, include_exp)
+ * (`sindy.py:42-77`). */
+typedef struct {
+  int32_t dim;          /* latent_dim d, 1..SB_MAX_DIM */
+  int32_t poly_order;   /* 1..SB_MAX_POLY */
+  int32_t include_sine; /* 0/1 */
+  int32_t include_exp;  /* 0/1 */
+} sb_library;
+
+/* sb_train_step `flags` and the packed fp64 output layout.
+ *   out[0]               = sum_{n,i} r[n,i]^2            with r = Θ(x)·Wᵀ − dx   (SB_STEP_LOSS)
+ *   out[1]               = n (number of samples reduced, as double)
+ *   out[2 .. 2+d*K)      = sum_n r[n,i]·Θ_k(x_n), row-major d×K  (SB_STEP_GRAD; the MSE gradient of
+ *                          `train.py:663-664,689` is 2/(n·d) times this)
+ *   then K*K doubles     = Gram ΘᵀΘ, row-major                    (SB_STEP_GRAM; `sindy.py:261` restated)
+ *   then K*d doubles     = ΘᵀẊ, row-major K×d                     (SB_STEP_B)
+ * Sections that are not requested are absent (the following ones move up). Sums, not means, so that
+ * shards on several GPUs combine with one all-reduce(sum). */
+#define SB_STEP_LOSS 1u
+#define SB_STEP_GRAD 2u
+#define SB_STEP_GRAM 4u
+#define SB_STEP_B 8u
+
+/* dtype tags for the rollout */
+#define SB_F32 0
+#define SB_F64 1
+/* integrators (`model_utils.py:223-255`) */
+#define SB_EULER 0
+#define SB_RK4 1
+
+int sb_version(void);
+const char* sb_last_error(void);
+
+/* Number of CUDA devices visible (0 if none / driver missing). */
+int sb_device_count(void);
+
+/* K = number of library columns; `sindy.py:179-189` get_term_num (extended to degree 5). <0 on error. */
+int sb_library_size(const sb_library* lib);
+/* Exponent table K×d (row-major) for the polynomial columns; sine rows hold -1 at their variable,
+ * exp rows -2 (others 0). Host memory. Mirrors the enumeration of `sindy.py:13-24`. */
+int sb_library_exponents(const sb_library* lib, int32_t* out_host);
+
+/* Bytes of device workspace any reducing call below may need for this library. */
+int64_t sb_workspace_bytes(const sb_library* lib);
+/* Number of doubles sb_train_step writes for `flags`. */
+int64_t sb_train_step_out_len(const sb_library* lib, uint32_t flags);
+
+/* Θ(x): `sindy.py:201-203` eval_Theta_at. x (n×d) → theta (n×K). Debug/parity only — the
+ * product paths never materialise Θ. */
+int sb_theta(const float* x, int64_t n, const sb_library* lib, float* theta, void* stream);
+
+/* h(x) = Θ(x)·Wᵀ with W = Ξ⊙mask (d×K): `sindy.py:79-82` forward. y (n×d). */
+int sb_forward(const float* x, int64_t n, const sb_library* lib, const float* w, float* y,
+               void* stream);
+
+/* Vector-Jacobian product of sb_forward (what autograd does for `loss.backward()`,
+ * `train.py:689`): gw[i,k] = sum_n gy[n,i]·Θ_k(x_n) (fp64, d×K; may be NULL) and
+ * gx[n,j] = sum_i gy[n,i] sum_k W[i,k] ∂Θ_k/∂x_j (n×d; may be NULL). */
+int sb_backward(const float* x, const float* gy, int64_t n, const sb_library* lib, const float* w,
+                double* gw, float* gx, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Jacobian-vector product J_h(x)·u = W·(J_Θ(x)·u): what `torch.autograd.functional.jvp(regressor, x, u)`
+ * computes by double-vjp in `model_utils.py:53-56` and `train.py:503-507`. out (n×d). */
+int sb_jvp(const float* x, const float* u, int64_t n, const sb_library* lib, const float* w,
+           float* out, void* stream);
+
+/* Vector-Jacobian product of sb_jvp w.r.t. (W, x, u) for cotangent g (n×d):
+ *   gw[i,k] = sum_n g[n,i]·(J_Θ(x_n)u_n)_k   (fp64 d×K, may be NULL)
+ *   gx      = Hessian-vector term sum_i g_i sum_k W_ik ∂²Θ_k/∂x∂x · u   (n×d, may be NULL)
+ *   gu      = J_h(x)ᵀ g                        (n×d, may be NULL)
+ * Needed because `symmreg_i` differentiates through its JVPs (`model_utils.py:32,56`). */
+int sb_jvp_backward(const float* x, const float* u, const float* g, int64_t n,
+                    const sb_library* lib, const float* w, double* gw, float* gx, float* gu,
+                    void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Fused train step: one pass over (x, dx) producing the sections selected by `flags` (layout above).
+ * Replaces `regressor(x)` + MSELoss + backward of the LBFGS closure (`train.py:645-690`) and the
+ * Θ/augmented-matrix build of `solve_SINDy_one_step` (`sindy.py:260-264`). dx may be NULL only if
+ * flags == SB_STEP_GRAM. w may be NULL if neither LOSS nor GRAD is requested. */
+int sb_train_step(const float* x, const float* dx, int64_t n, const sb_library* lib,
+                  const float* w, uint32_t flags, double* out, void* workspace,
+                  int64_t workspace_bytes, void* stream);
+
+/* Name of the kernel variant sb_train_step would dispatch for this library ("fused_tma<3,5>",
+ * "generic" ...). Static string. */
+const char* sb_train_step_variant(const sb_library* lib, uint32_t flags);
+
+/* Fixed-step rollout of dx/dt = Θ(x)·Wᵀ for every initial condition in lock-step.
+ *  - `model_utils.py:223-255` odeint (dtype SB_F32; method SB_EULER / SB_RK4; record_dx = 0):
+ *      states after step s for s = stride, 2·stride, ... are written to x_out[(s/stride − 1), ic, :]
+ *      (x0 itself is NOT stored, as `full_traj` there); x_last (n_ics×d, may be NULL) gets the final state.
+ *  - `data_utils/ode.py:7-28` solve_ode_batch (dtype SB_F64, SB_RK4, record_dx = 1):
+ *      n_steps counts stored rows INCLUDING x0: row s (s % stride == 0) holds x after s steps and
+ *      dx_out the RHS there; only n_steps − 1 updates are made.
+ * x0, w, outputs are float or double according to `dtype`. Outputs have leading dimension
+ * n_rows = rows stored, then n_ics, then d. x_out / dx_out may be NULL. */
+int sb_rollout(const void* x0, int64_t n_ics, const sb_library* lib, const void* w, double dt,
+               int64_t n_steps, int64_t stride, int method, int dtype, int record_dx,
+               void* x_out, void* dx_out, void* x_last, void* stream);
+
+/* WSINDy weak-form integrals with trigonometric test functions (`sindy.py:332-347,361-362`):
+ *   V[j,t]  = dt·sqrt(2/T)·sin((j+1)π t/T),  V'[j,t] = dt·sqrt(2/T)·(j+1)π/T·cos((j+1)π t/T),  t = t_idx·dt
+ *   G[traj,j,k] = sum_t V[j,t]·Θ_k(x[traj,t]),   b[traj,j,i] = −sum_t V'[j,t]·x[traj,t,i]
+ * x is (n_traj × T × d); test functions are generated on the fly in fp32 with the reference's
+ * operation order. G (n_traj×n_test×K) and b (n_traj×n_test×d) are fp64. */
+int sb_wsindy_integrals(const float* x, int64_t n_traj, int64_t T, const sb_library* lib, float dt,
+                        double t_max, int n_test, double* G, double* b, void* stream);
+
+/* FP32 FMA-pipe peak microbenchmark used for the roofline denominator (not in MEASURED_PEAKS.json):
+ * variant 0 = scalar FFMA, 1 = packed FFMA2 (fma.rn.f32x2), 2 = FFMA2 with a constant-bank operand.
+ * Runs on `stream`, writes the achieved TFLOP/s (2 flop per lane-FMA) to *tflops_host. Synchronises. */
+int sb_fp32_peak(int variant, int iters, double* tflops_host, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SINDY_B200_H */

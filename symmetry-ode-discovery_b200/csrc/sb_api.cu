@@ -1,0 +1,236 @@
+// sb_api.cu — the extern "C" surface declared in include/sindy_b200.h: argument validation,
+// library-table construction and dispatch between the specialised and the generic kernels.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "sb_common.cuh"
+
+namespace sb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+  return SB_ERR_CUDA;
+}
+
+int build_table(const sb_library* lib, LibTab* tab) {
+  if (!lib) { set_error("library is NULL"); return SB_ERR_INVALID; }
+  const int d = lib->dim, p = lib->poly_order;
+  if (d < 1 || d > SB_MAX_DIM) { set_error("dim=%d outside 1..%d", d, SB_MAX_DIM); return SB_ERR_UNSUPPORTED; }
+  if (p < 1 || p > SB_MAX_POLY) { set_error("poly_order=%d outside 1..%d", p, SB_MAX_POLY); return SB_ERR_UNSUPPORTED; }
+  const int n_poly = n_poly_terms(d, p);
+  const int K = n_poly + (lib->include_sine ? d : 0) + (lib->include_exp ? d : 0);
+  if (K > SB_MAX_TERMS) { set_error("library has %d columns, max %d", K, SB_MAX_TERMS); return SB_ERR_UNSUPPORTED; }
+  memset(tab, 0, sizeof(*tab));
+  tab->d = d; tab->K = K; tab->n_poly = n_poly;
+  tab->sine = lib->include_sine ? 1 : 0; tab->exp_ = lib->include_exp ? 1 : 0;
+  // same recurrence as make_poly_tab (children of parent p are p*x_j for j >= last variable of p)
+  int last[SB_MAX_TERMS];
+  int k = 0;
+  tab->parent[k] = 0; tab->var[k] = 0; last[k] = 0; ++k;
+  int prev_begin = k;
+  for (int j = 0; j < d; ++j) { tab->parent[k] = 0; tab->var[k] = (unsigned char)j; last[k] = j; ++k; }
+  for (int n = 2; n <= p; ++n) {
+    const int pb = prev_begin, pe = k;
+    prev_begin = k;
+    for (int q = pb; q < pe; ++q)
+      for (int j = last[q]; j < d; ++j) { tab->parent[k] = (unsigned char)q; tab->var[k] = (unsigned char)j; last[k] = j; ++k; }
+  }
+  if (k != n_poly) { set_error("internal: enumerated %d polynomial terms, expected %d", k, n_poly); return SB_ERR_INVALID; }
+  return SB_OK;
+}
+
+static int check_ptr(const void* p, const char* name) {
+  if (!p) { set_error("%s is NULL", name); return SB_ERR_INVALID; }
+  return SB_OK;
+}
+
+}  // namespace sb
+
+using namespace sb;
+
+#define SB_TRY(expr) do { int _s = (expr); if (_s != SB_OK) return _s; } while (0)
+
+extern "C" {
+
+int sb_version(void) { return 100; }
+
+const char* sb_last_error(void) { return g_err; }
+
+int sb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int sb_library_size(const sb_library* lib) {
+  LibTab t;
+  int s = build_table(lib, &t);
+  return s == SB_OK ? t.K : s;
+}
+
+int sb_library_exponents(const sb_library* lib, int32_t* out) {
+  LibTab t;
+  SB_TRY(build_table(lib, &t));
+  SB_TRY(check_ptr(out, "out_host"));
+  memset(out, 0, sizeof(int32_t) * (size_t)t.K * t.d);
+  for (int k = 1; k < t.n_poly; ++k) {
+    for (int j = 0; j < t.d; ++j) out[k * t.d + j] = out[t.parent[k] * t.d + j];
+    out[k * t.d + t.var[k]] += 1;
+  }
+  int k = t.n_poly;
+  if (t.sine) for (int j = 0; j < t.d; ++j, ++k) out[k * t.d + j] = -1;
+  if (t.exp_) for (int j = 0; j < t.d; ++j, ++k) out[k * t.d + j] = -2;
+  return SB_OK;
+}
+
+int64_t sb_workspace_bytes(const sb_library* lib) {
+  LibTab t;
+  int s = build_table(lib, &t);
+  if (s != SB_OK) return s;
+  int64_t a = generic_workspace_bytes(t), b = fused_workspace_bytes(t);
+  return a > b ? a : b;
+}
+
+int64_t sb_train_step_out_len(const sb_library* lib, uint32_t flags) {
+  LibTab t;
+  int s = build_table(lib, &t);
+  if (s != SB_OK) return s;
+  int64_t len = 2;
+  if (flags & SB_STEP_GRAD) len += (int64_t)t.d * t.K;
+  if (flags & SB_STEP_GRAM) len += (int64_t)t.K * t.K;
+  if (flags & SB_STEP_B) len += (int64_t)t.K * t.d;
+  return len;
+}
+
+int sb_theta(const float* x, int64_t n, const sb_library* lib, float* theta, void* stream) {
+  LibTab t;
+  SB_TRY(build_table(lib, &t));
+  if (n < 0) { set_error("n=%lld < 0", (long long)n); return SB_ERR_INVALID; }
+  if (n == 0) return SB_OK;
+  SB_TRY(check_ptr(x, "x")); SB_TRY(check_ptr(theta, "theta"));
+  return generic_theta(x, n, t, theta, (cudaStream_t)stream);
+}
+
+int sb_forward(const float* x, int64_t n, const sb_library* lib, const float* w, float* y, void* stream) {
+  LibTab t;
+  SB_TRY(build_table(lib, &t));
+  if (n < 0) { set_error("n=%lld < 0", (long long)n); return SB_ERR_INVALID; }
+  if (n == 0) return SB_OK;
+  SB_TRY(check_ptr(x, "x")); SB_TRY(check_ptr(w, "w")); SB_TRY(check_ptr(y, "y"));
+  return generic_forward(x, n, t, w, y, (cudaStream_t)stream);
+}
+
+int sb_jvp(const float* x, const float* u, int64_t n, const sb_library* lib, const float* w, float* out,
+           void* stream) {
+  LibTab t;
+  SB_TRY(build_table(lib, &t));
+  if (n < 0) { set_error("n=%lld < 0", (long long)n); return SB_ERR_INVALID; }
+  if (n == 0) return SB_OK;
+  SB_TRY(check_ptr(x, "x")); SB_TRY(check_ptr(u, "u")); SB_TRY(check_ptr(w, "w")); SB_TRY(check_ptr(out, "out"));
+  return generic_jvp(x, u, n, t, w, out, (cudaStream_t)stream);
+}
+
+int sb_backward(const float* x, const float* gy, int64_t n, const sb_library* lib, const float* w,
+                double* gw, float* gx, void* ws, int64_t ws_bytes, void* stream) {
+  LibTab t;
+  SB_TRY(build_table(lib, &t));
+  if (n < 0) { set_error("n=%lld < 0", (long long)n); return SB_ERR_INVALID; }
+  if (!gw && !gx) return SB_OK;
+  if (n > 0) { SB_TRY(check_ptr(x, "x")); SB_TRY(check_ptr(gy, "gy")); }
+  if (gx) SB_TRY(check_ptr(w, "w"));
+  if (gw) SB_TRY(check_ptr(ws, "workspace"));
+  return generic_backward(x, gy, n, t, w, gw, gx, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int sb_jvp_backward(const float* x, const float* u, const float* g, int64_t n, const sb_library* lib,
+                    const float* w, double* gw, float* gx, float* gu, void* ws, int64_t ws_bytes,
+                    void* stream) {
+  LibTab t;
+  SB_TRY(build_table(lib, &t));
+  if (n < 0) { set_error("n=%lld < 0", (long long)n); return SB_ERR_INVALID; }
+  if (!gw && !gx && !gu) return SB_OK;
+  if (n > 0) { SB_TRY(check_ptr(x, "x")); SB_TRY(check_ptr(u, "u")); SB_TRY(check_ptr(g, "g")); }
+  if (gx || gu) SB_TRY(check_ptr(w, "w"));
+  if (gw) SB_TRY(check_ptr(ws, "workspace"));
+  return generic_jvp_backward(x, u, g, n, t, w, gw, gx, gu, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+static int step_args_ok(const float* x, const float* dx, int64_t n, const float* w, uint32_t flags,
+                        double* out, void* ws) {
+  if (n < 0) { set_error("n=%lld < 0", (long long)n); return SB_ERR_INVALID; }
+  if (flags == 0 || (flags & ~(SB_STEP_LOSS | SB_STEP_GRAD | SB_STEP_GRAM | SB_STEP_B))) {
+    set_error("bad flags 0x%x", flags); return SB_ERR_INVALID;
+  }
+  SB_TRY(check_ptr(out, "out")); SB_TRY(check_ptr(ws, "workspace"));
+  if (n > 0) SB_TRY(check_ptr(x, "x"));
+  if (n > 0 && (flags & (SB_STEP_LOSS | SB_STEP_GRAD | SB_STEP_B))) SB_TRY(check_ptr(dx, "dx"));
+  if (flags & (SB_STEP_LOSS | SB_STEP_GRAD)) SB_TRY(check_ptr(w, "w"));
+  return SB_OK;
+}
+
+int sb_train_step(const float* x, const float* dx, int64_t n, const sb_library* lib, const float* w,
+                  uint32_t flags, double* out, void* ws, int64_t ws_bytes, void* stream) {
+  LibTab t;
+  SB_TRY(build_table(lib, &t));
+  SB_TRY(step_args_ok(x, dx, n, w, flags, out, ws));
+  // the TMA-staged kernels need 16-byte aligned, contiguous x / dx
+  const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dx)) & 15u) == 0;
+  if (n > 0 && aligned && fused_supported(t, flags))
+    return fused_train_step(x, dx, n, t, w, flags, out, ws, ws_bytes, (cudaStream_t)stream);
+  return generic_train_step(x, dx, n, t, w, flags, out, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+const char* sb_train_step_variant(const sb_library* lib, uint32_t flags) {
+  LibTab t;
+  if (build_table(lib, &t) != SB_OK) return "unsupported";
+  return fused_supported(t, flags) ? fused_variant_name(t, flags) : "generic";
+}
+
+int sb_rollout(const void* x0, int64_t n_ics, const sb_library* lib, const void* w, double dt,
+               int64_t n_steps, int64_t stride, int method, int dtype, int record_dx, void* x_out,
+               void* dx_out, void* x_last, void* stream) {
+  LibTab t;
+  SB_TRY(build_table(lib, &t));
+  if (n_ics < 0 || n_steps < 0 || stride < 1) {
+    set_error("bad rollout sizes n_ics=%lld n_steps=%lld stride=%lld", (long long)n_ics, (long long)n_steps,
+              (long long)stride);
+    return SB_ERR_INVALID;
+  }
+  if (method != SB_EULER && method != SB_RK4) { set_error("unknown method %d", method); return SB_ERR_INVALID; }
+  if (dtype != SB_F32 && dtype != SB_F64) { set_error("unknown dtype %d", dtype); return SB_ERR_INVALID; }
+  if (n_ics == 0) return SB_OK;
+  SB_TRY(check_ptr(x0, "x0")); SB_TRY(check_ptr(w, "w"));
+  return rollout(x0, n_ics, t, w, dt, n_steps, stride, method, dtype, record_dx, x_out, dx_out, x_last,
+                 (cudaStream_t)stream);
+}
+
+int sb_wsindy_integrals(const float* x, int64_t n_traj, int64_t T, const sb_library* lib, float dt,
+                        double t_max, int n_test, double* G, double* b, void* stream) {
+  LibTab t;
+  SB_TRY(build_table(lib, &t));
+  if (n_traj < 0 || T < 0 || n_test < 1 || n_test > 1024) {
+    set_error("bad wsindy sizes n_traj=%lld T=%lld n_test=%d", (long long)n_traj, (long long)T, n_test);
+    return SB_ERR_INVALID;
+  }
+  if (n_traj == 0) return SB_OK;
+  SB_TRY(check_ptr(x, "x")); SB_TRY(check_ptr(G, "G")); SB_TRY(check_ptr(b, "b"));
+  return wsindy_integrals(x, n_traj, T, t, dt, t_max, n_test, G, b, (cudaStream_t)stream);
+}
+
+int sb_fp32_peak(int variant, int iters, double* tflops_host, void* stream) {
+  SB_TRY(check_ptr(tflops_host, "tflops_host"));
+  if (variant < 0 || variant > 2 || iters < 1) { set_error("bad variant/iters"); return SB_ERR_INVALID; }
+  return fp32_peak(variant, iters, tflops_host, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,187 @@
+// sb_common.cuh — shared internals of libsindy_b200.so (not part of the ABI).
+//
+// Library enumeration follows the reference's `sindy.py:7-30` (SINDyConst/Poly1/Poly2/Poly3/Sine/Exp):
+// degree-n monomials over non-decreasing index tuples in lexicographic order, each formed left to right,
+// i.e. column(i1..in) = column(i1..i(n-1)) * x[in]. That recurrence (parent column, variable) is the only
+// table the kernels need: values, Jacobian-vector and Hessian-vector sweeps all run over it.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <type_traits>
+#include <utility>
+
+#include "../../include/sindy_b200.h"
+
+namespace sb {
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define SB_CUDA_TRY(expr)                                         \
+  do {                                                            \
+    cudaError_t _e = (expr);                                      \
+    if (_e != cudaSuccess) return ::sb::cuda_fail(_e, #expr);     \
+  } while (0)
+
+#define SB_LAUNCH_CHECK(name)                                     \
+  do {                                                            \
+    cudaError_t _e = cudaGetLastError();                          \
+    if (_e != cudaSuccess) return ::sb::cuda_fail(_e, name);      \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// runtime library table (kernel parameter of the generic kernels; ~540 bytes)
+// ---------------------------------------------------------------------------------------------
+struct LibTab {
+  int d;       // state dimension
+  int K;       // total columns
+  int n_poly;  // polynomial columns (1 + d + ...)
+  int sine;    // 0/1
+  int exp_;    // 0/1
+  unsigned char parent[SB_MAX_TERMS];  // parent column of polynomial column k (k > d)
+  unsigned char var[SB_MAX_TERMS];     // variable multiplied onto the parent
+};
+
+// Number of monomials of degree exactly n in d variables: C(n+d-1, d-1).
+constexpr int n_monomials(int d, int n) {
+  long long r = 1;
+  for (int i = 1; i <= d - 1; ++i) r = r * (n + i) / i;
+  return (int)r;
+}
+constexpr int n_poly_terms(int d, int p) {
+  int k = 0;
+  for (int n = 0; n <= p; ++n) k += n_monomials(d, n);
+  return k;
+}
+
+// Validates `lib` and fills `tab`. Returns SB_OK or an error status.
+int build_table(const sb_library* lib, LibTab* tab);
+
+// ---------------------------------------------------------------------------------------------
+// compile-time library tables for the specialised kernels
+// ---------------------------------------------------------------------------------------------
+template <int D, int P>
+struct PolyTab {
+  static constexpr int K = n_poly_terms(D, P);
+  int parent[K];
+  int var[K];
+  int degree[K];
+  int block_begin[P + 2];  // first column of each degree block; block_begin[P+1] = K
+};
+
+template <int D, int P>
+constexpr PolyTab<D, P> make_poly_tab() {
+  PolyTab<D, P> t{};
+  constexpr int K = PolyTab<D, P>::K;
+  int last[K] = {};  // last (largest) variable index of each column's tuple
+  t.parent[0] = 0; t.var[0] = 0; t.degree[0] = 0; last[0] = 0;
+  t.block_begin[0] = 0;
+  t.block_begin[1] = 1;
+  int k = 1;
+  for (int j = 0; j < D; ++j) { t.parent[k] = 0; t.var[k] = j; t.degree[k] = 1; last[k] = j; ++k; }
+  for (int n = 2; n <= P; ++n) {
+    t.block_begin[n] = k;
+    const int pb = t.block_begin[n - 1], pe = k;
+    for (int p = pb; p < pe; ++p)
+      for (int j = last[p]; j < D; ++j) { t.parent[k] = p; t.var[k] = j; t.degree[k] = n; last[k] = j; ++k; }
+  }
+  t.block_begin[P + 1] = k;
+  return t;
+}
+
+template <int D, int P>
+struct Poly {
+  static constexpr int K = PolyTab<D, P>::K;
+  static constexpr PolyTab<D, P> tab = make_poly_tab<D, P>();
+};
+
+// compile-time loop: f(std::integral_constant<int, I>) for I in [B, E)
+template <int B, int E, class F>
+__host__ __device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (B < E) {
+    f(std::integral_constant<int, B>{});
+    static_for<B + 1, E>(static_cast<F&&>(f));
+  }
+}
+
+// Θ(x) for a polynomial library, fully unrolled: m[k] = m[parent] * x[var]  (`sindy.py:13-24`)
+template <int D, int P, class T>
+__device__ __forceinline__ void expand_poly(const T (&x)[D], T (&m)[Poly<D, P>::K]) {
+  using L = Poly<D, P>;
+  m[0] = T(1);
+  static_for<0, D>([&](auto j) { m[1 + j] = x[j]; });
+  static_for<1 + D, L::K>([&](auto kc) {
+    constexpr int k = kc;
+    constexpr int p = L::tab.parent[k];
+    constexpr int v = L::tab.var[k];
+    m[k] = m[p] * x[v];
+  });
+}
+
+// ---------------------------------------------------------------------------------------------
+// reductions
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Workspace header: one ticket counter (must be zero before the first call; every reducing kernel
+// resets it before exiting), padded to 256 bytes; partial sums follow.
+constexpr int64_t kWsHeaderBytes = 256;
+
+// Grid-size cap used by every reducing kernel (partials per output row).
+constexpr int kMaxPartialBlocks = 148 * 4;
+
+// ---------------------------------------------------------------------------------------------
+// constant-memory coefficient slots (W = Ξ⊙mask), filled by stream-ordered D2D copies
+// ---------------------------------------------------------------------------------------------
+constexpr int kConstW = SB_MAX_DIM * SB_MAX_TERMS;  // 2048 floats = 8 KB
+
+// ---------------------------------------------------------------------------------------------
+// internal entry points (one per translation unit)
+// ---------------------------------------------------------------------------------------------
+// generic (runtime-table) path
+int generic_theta(const float* x, int64_t n, const LibTab& t, float* theta, cudaStream_t s);
+int generic_forward(const float* x, int64_t n, const LibTab& t, const float* w, float* y, cudaStream_t s);
+int generic_jvp(const float* x, const float* u, int64_t n, const LibTab& t, const float* w, float* out,
+                cudaStream_t s);
+int generic_backward(const float* x, const float* gy, int64_t n, const LibTab& t, const float* w,
+                     double* gw, float* gx, void* ws, int64_t ws_bytes, cudaStream_t s);
+int generic_jvp_backward(const float* x, const float* u, const float* g, int64_t n, const LibTab& t,
+                         const float* w, double* gw, float* gx, float* gu, void* ws, int64_t ws_bytes,
+                         cudaStream_t s);
+int generic_train_step(const float* x, const float* dx, int64_t n, const LibTab& t, const float* w,
+                       uint32_t flags, double* out, void* ws, int64_t ws_bytes, cudaStream_t s);
+int64_t generic_workspace_bytes(const LibTab& t);
+
+// specialised (compile-time library, register-resident, TMA-staged) fused train step
+bool fused_supported(const LibTab& t, uint32_t flags);
+const char* fused_variant_name(const LibTab& t, uint32_t flags);
+int fused_train_step(const float* x, const float* dx, int64_t n, const LibTab& t, const float* w,
+                     uint32_t flags, double* out, void* ws, int64_t ws_bytes, cudaStream_t s);
+int64_t fused_workspace_bytes(const LibTab& t);
+
+// rollout
+int rollout(const void* x0, int64_t n_ics, const LibTab& t, const void* w, double dt, int64_t n_steps,
+            int64_t stride, int method, int dtype, int record_dx, void* x_out, void* dx_out, void* x_last,
+            cudaStream_t s);
+
+// WSINDy integrals
+int wsindy_integrals(const float* x, int64_t n_traj, int64_t T, const LibTab& t, float dt, double t_max,
+                     int n_test, double* G, double* b, cudaStream_t s);
+
+// FP32 peak microbenchmark
+int fp32_peak(int variant, int iters, double* tflops_host, cudaStream_t s);
+
+}  // namespace sb

@@ -1,0 +1,366 @@
+// sb_fused.cu — register-resident fused SINDy train step for the hot polynomial libraries.
+//
+// Replaces, in ONE pass over (x, dx), the reference's `regressor(x)` (Θ materialised column by column,
+// `sindy.py:79-82`), `MSELoss` (`train.py:663-664`) and the Θ-side of `loss.backward()` (`train.py:689`):
+//   r = Θ(x)·Wᵀ − dx,   out = { Σ r², Σ_n r_i Θ_k }.
+// Θ never exists in memory: each thread expands the K monomials of its sample in registers by the
+// parent*variable recurrence, forms the d predictions, and accumulates the d×K outer product r ⊗ Θ into
+// private fp32 accumulators. All d·K FMAs of the prediction and of the gradient are issued as packed
+// `fma.rn.f32x2` (SASS FFMA2: two fp32 FMAs per lane per issue slot) over adjacent library columns; W comes
+// from the constant bank (uniform datapath), so the only vector-register operands are Θ pairs, r and the
+// accumulators.
+//
+// Data movement: x and dx tiles are streamed HBM -> shared memory with 1-D TMA bulk copies
+// (cp.async.bulk ... mbarrier::complete_tx, SASS UBLKCP) into a kStages-deep ring, one elected thread issuing,
+// every thread waiting on the stage's mbarrier; X and dX are read exactly once, 8·d bytes per sample.
+// Grid = resident CTAs (multiple of the SM count), static round-robin tile assignment, per-CTA partials in
+// fp64 and an ordered last-block reduction => deterministic results.
+#include "sb_common.cuh"
+
+namespace sb {
+
+namespace {
+
+__constant__ float2 c_w2[kConstW / 2];
+
+// ---- PTX wrappers -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  }
+}
+
+// ---- configuration per library ------------------------------------------------------------------
+template <int D, int P>
+struct Cfg {
+  static constexpr int K = Poly<D, P>::K;
+  static constexpr int K2 = (K + 1) / 2;     // packed column pairs
+  static constexpr int NV = D * K + 1;       // values reduced per CTA (grad + loss)
+  static constexpr int kThreads = 256;
+  static constexpr int kTile = 1024;         // samples per stage
+  static constexpr int kStages = 4;
+  // accumulators dominate the register budget: D*K2*2 of them
+  static constexpr int kMinBlocks = (D * K2 * 2 + K > 150) ? 1 : ((D * K2 * 2 + K > 40) ? 2 : 3);
+  static constexpr size_t kSmemData = (size_t)kStages * 2 * kTile * D * sizeof(float);
+  static constexpr size_t kSmemBytes = kSmemData + kStages * sizeof(uint64_t) + 16;
+};
+
+enum { LEFT_RESIDUAL = 0, LEFT_DX = 1 };
+
+// one sample: expand Θ, predict, accumulate r ⊗ Θ
+template <int D, int P, int LEFT>
+__device__ __forceinline__ void accumulate_sample(const float (&xs)[D], const float (&ds)[D],
+                                                  float2 (&acc)[D][Cfg<D, P>::K2], float& lacc) {
+  using C = Cfg<D, P>;
+  float m[C::K];
+  expand_poly<D, P>(xs, m);
+  float2 m2[C::K2];
+  static_for<0, C::K2>([&](auto kc) {
+    constexpr int kk = kc;
+    m2[kk] = make_float2(m[2 * kk], (2 * kk + 1 < C::K) ? m[2 * kk + 1] : 0.f);
+  });
+  float r[D];
+  if constexpr (LEFT == LEFT_RESIDUAL) {
+    float2 pred[D];
+    static_for<0, D>([&](auto i) { pred[i] = make_float2(0.f, 0.f); });
+    static_for<0, C::K2>([&](auto kc) {
+      constexpr int kk = kc;
+      static_for<0, D>([&](auto ic) {
+        constexpr int i = ic;
+        pred[i] = __ffma2_rn(c_w2[i * C::K2 + kk], m2[kk], pred[i]);
+      });
+    });
+    static_for<0, D>([&](auto i) {
+      r[i] = (pred[i].x + pred[i].y) - ds[i];
+      lacc = fmaf(r[i], r[i], lacc);
+    });
+  } else {
+    static_for<0, D>([&](auto i) { r[i] = ds[i]; });
+  }
+  static_for<0, D>([&](auto ic) {
+    constexpr int i = ic;
+    const float2 r2 = make_float2(r[i], r[i]);
+    static_for<0, C::K2>([&](auto kc) {
+      constexpr int kk = kc;
+      acc[i][kk] = __ffma2_rn(r2, m2[kk], acc[i][kk]);
+    });
+  });
+}
+
+struct FusedArgs {
+  const float* x;
+  const float* dx;
+  int64_t n;          // samples
+  int64_t n_bulk;     // samples covered by TMA tiles (multiple of 4)
+  int64_t n_tiles;
+  double* partial;    // [grid][NV]
+  unsigned int* ticket;
+  double* out;        // packed output base
+  int64_t out_off;    // offset of this section's d×K block
+  int out_transposed; // 0: [i*K+k], 1: [k*d+i]  (b section)
+  int write_header;   // write out[0] (loss) and out[1] (n)
+};
+
+template <int D, int P, int LEFT>
+__global__ void __launch_bounds__(Cfg<D, P>::kThreads, Cfg<D, P>::kMinBlocks)
+fused_step_kernel(FusedArgs a) {
+  using C = Cfg<D, P>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* tiles = reinterpret_cast<float*>(smem_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + C::kSmemData);
+  __shared__ float red[C::kThreads / 32][C::NV];
+  __shared__ int is_last;
+
+  const int tid = threadIdx.x;
+  constexpr int kTileFloats = C::kTile * D;
+
+  auto tile_count = [&](int64_t tile) -> int {
+    const int64_t rem = a.n_bulk - tile * C::kTile;
+    return (int)(rem < C::kTile ? rem : C::kTile);
+  };
+  auto issue = [&](int64_t tile, int stage) {
+    const int cnt = tile_count(tile);
+    const uint32_t bytes = (uint32_t)cnt * D * sizeof(float);
+    float* sx = tiles + (size_t)stage * 2 * kTileFloats;
+    mbar_expect_tx(&full[stage], 2 * bytes);
+    tma_load_1d(sx, a.x + tile * (int64_t)kTileFloats, bytes, &full[stage]);
+    tma_load_1d(sx + kTileFloats, a.dx + tile * (int64_t)kTileFloats, bytes, &full[stage]);
+  };
+
+  if (tid == 0) {
+    for (int s = 0; s < C::kStages; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int s = 0; s < C::kStages; ++s) {
+      const int64_t tile = blockIdx.x + (int64_t)s * gridDim.x;
+      if (tile < a.n_tiles) issue(tile, s);
+    }
+  }
+
+  float2 acc[D][C::K2];
+  static_for<0, D>([&](auto i) {
+    static_for<0, C::K2>([&](auto kk) { acc[i][kk] = make_float2(0.f, 0.f); });
+  });
+  float lacc = 0.f;
+
+  int it = 0;
+  for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+    const int stage = it % C::kStages;
+    const uint32_t parity = (uint32_t)(it / C::kStages) & 1u;
+    mbar_wait(&full[stage], parity);
+    const float* sx = tiles + (size_t)stage * 2 * kTileFloats;
+    const float* sd = sx + kTileFloats;
+    const int cnt = tile_count(tile);
+#pragma unroll 1
+    for (int j = tid; j < cnt; j += C::kThreads) {
+      float xs[D], ds[D];
+      static_for<0, D>([&](auto q) { xs[q] = sx[j * D + q]; ds[q] = sd[j * D + q]; });
+      accumulate_sample<D, P, LEFT>(xs, ds, acc, lacc);
+    }
+    __syncthreads();  // every thread is done with this stage before it is refilled
+    if (tid == 0) {
+      const int64_t next = tile + (int64_t)C::kStages * gridDim.x;
+      if (next < a.n_tiles) issue(next, stage);
+    }
+  }
+
+  // ragged tail (n % 4 samples) straight from global memory, by the first threads of block 0
+  if (blockIdx.x == 0) {
+    const int64_t j = a.n_bulk + tid;
+    if (j < a.n) {
+      float xs[D], ds[D];
+      static_for<0, D>([&](auto q) { xs[q] = __ldg(a.x + j * D + q); ds[q] = __ldg(a.dx + j * D + q); });
+      accumulate_sample<D, P, LEFT>(xs, ds, acc, lacc);
+    }
+  }
+
+  // ---- CTA reduction: shuffles within the warp, fp64 across warps ----
+  const int lane = tid & 31, wid = tid >> 5;
+  static_for<0, D>([&](auto ic) {
+    constexpr int i = ic;
+    static_for<0, C::K2>([&](auto kc) {
+      constexpr int kk = kc;
+      const float vx = warp_sum(acc[i][kk].x);
+      const float vy = warp_sum(acc[i][kk].y);
+      if (lane == 0) {
+        red[wid][i * C::K + 2 * kk] = vx;
+        if (2 * kk + 1 < C::K) red[wid][i * C::K + 2 * kk + 1] = vy;
+      }
+    });
+  });
+  {
+    const float v = warp_sum(lacc);
+    if (lane == 0) red[wid][C::NV - 1] = v;
+  }
+  __syncthreads();
+  double* mine = a.partial + (int64_t)blockIdx.x * C::NV;
+  for (int e = tid; e < C::NV; e += C::kThreads) {
+    double v = 0.0;
+#pragma unroll
+    for (int wq = 0; wq < C::kThreads / 32; ++wq) v += (double)red[wq][e];
+    mine[e] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) is_last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1u);
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+
+  // ---- ordered final reduction over CTAs ----
+  for (int e = tid; e < C::NV; e += C::kThreads) {
+    double v = 0.0;
+    for (unsigned int b = 0; b < gridDim.x; ++b) v += a.partial[(int64_t)b * C::NV + e];
+    if (e == C::NV - 1) {
+      if (a.write_header) { a.out[0] = v; a.out[1] = (double)a.n; }
+    } else {
+      const int i = e / C::K, k = e % C::K;
+      a.out[a.out_off + (a.out_transposed ? (int64_t)k * D + i : (int64_t)e)] = v;
+    }
+  }
+  if (tid == 0) *a.ticket = 0u;
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+template <int D, int P, int LEFT>
+int launch_fused(FusedArgs a, void* ws, int64_t ws_bytes, cudaStream_t s) {
+  using C = Cfg<D, P>;
+  auto kern = fused_step_kernel<D, P, LEFT>;
+  static int grid_cached[64] = {0};  // per device
+  int dev = 0;
+  SB_CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) { set_error("device index %d out of range", dev); return SB_ERR_INVALID; }
+  if (grid_cached[dev] == 0) {
+    SB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes));
+    int per_sm = 0, sms = 0;
+    SB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::kThreads, C::kSmemBytes));
+    SB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (per_sm < 1) { set_error("fused kernel <%d,%d> does not fit on an SM", D, P); return SB_ERR_CUDA; }
+    int g = per_sm * sms;
+    if (g > kMaxPartialBlocks) g = kMaxPartialBlocks;
+    grid_cached[dev] = g;
+  }
+  a.n_bulk = a.n & ~(int64_t)3;
+  a.n_tiles = (a.n_bulk + C::kTile - 1) / C::kTile;
+  int64_t grid = a.n_tiles < grid_cached[dev] ? a.n_tiles : grid_cached[dev];
+  if (grid < 1) grid = 1;
+  const int64_t need = kWsHeaderBytes + grid * C::NV * (int64_t)sizeof(double);
+  if (ws_bytes < need) {
+    set_error("workspace too small: %lld < %lld bytes", (long long)ws_bytes, (long long)need);
+    return SB_ERR_WORKSPACE;
+  }
+  a.ticket = reinterpret_cast<unsigned int*>(ws);
+  a.partial = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + kWsHeaderBytes);
+  kern<<<(unsigned)grid, C::kThreads, C::kSmemBytes, s>>>(a);
+  SB_LAUNCH_CHECK("fused_step_kernel");
+  return SB_OK;
+}
+
+// W (d×K fp32, device) -> packed constant slot, stream-ordered
+template <int D, int P>
+int upload_w(const float* w, cudaStream_t s) {
+  using C = Cfg<D, P>;
+  if (C::K % 2 == 0) {
+    SB_CUDA_TRY(cudaMemcpyToSymbolAsync(c_w2, w, sizeof(float) * D * C::K, 0, cudaMemcpyDeviceToDevice, s));
+  } else {
+    void* base = nullptr;
+    SB_CUDA_TRY(cudaGetSymbolAddress(&base, c_w2));
+    SB_CUDA_TRY(cudaMemsetAsync(base, 0, sizeof(float2) * D * C::K2, s));
+    for (int i = 0; i < D; ++i)
+      SB_CUDA_TRY(cudaMemcpyToSymbolAsync(c_w2, w + i * C::K, sizeof(float) * C::K,
+                                          sizeof(float2) * (size_t)i * C::K2, cudaMemcpyDeviceToDevice, s));
+  }
+  return SB_OK;
+}
+
+template <int D, int P>
+int run_fused(const float* x, const float* dx, int64_t n, const float* w, uint32_t flags, double* out, void* ws,
+              int64_t ws_bytes, cudaStream_t s) {
+  using C = Cfg<D, P>;
+  FusedArgs a{};
+  a.x = x; a.dx = dx; a.n = n; a.out = out;
+  const bool resid = flags & (SB_STEP_LOSS | SB_STEP_GRAD);
+  if (resid) {
+    int st = upload_w<D, P>(w, s);
+    if (st != SB_OK) return st;
+    a.out_off = 2; a.out_transposed = 0; a.write_header = 1;
+    st = launch_fused<D, P, LEFT_RESIDUAL>(a, ws, ws_bytes, s);
+    if (st != SB_OK) return st;
+  }
+  if (flags & SB_STEP_B) {
+    a.out_off = 2 + ((flags & SB_STEP_GRAD) ? (int64_t)D * C::K : 0);
+    a.out_transposed = 1; a.write_header = resid ? 0 : 1;
+    int st = launch_fused<D, P, LEFT_DX>(a, ws, ws_bytes, s);
+    if (st != SB_OK) return st;
+  }
+  return SB_OK;
+}
+
+// the list of specialised libraries (polynomial only)
+#define SB_FUSED_SHAPES(X) X(2, 2) X(2, 3) X(3, 2) X(3, 3) X(3, 5)
+
+}  // namespace
+
+bool fused_supported(const LibTab& t, uint32_t flags) {
+  if (t.sine || t.exp_) return false;
+  if (flags & SB_STEP_GRAM) return false;
+  // LOSS without GRAD still runs the residual kernel (the gradient section is simply not reported)
+  if ((flags & SB_STEP_LOSS) && !(flags & SB_STEP_GRAD)) return false;
+#define X(D, P) if (t.d == D && t.n_poly == n_poly_terms(D, P)) return true;
+  SB_FUSED_SHAPES(X)
+#undef X
+  return false;
+}
+
+const char* fused_variant_name(const LibTab& t, uint32_t flags) {
+  (void)flags;
+#define X(D, P) if (t.d == D && t.n_poly == n_poly_terms(D, P)) return "fused_tma<" #D "," #P ">";
+  SB_FUSED_SHAPES(X)
+#undef X
+  return "generic";
+}
+
+int64_t fused_workspace_bytes(const LibTab& t) {
+  return kWsHeaderBytes + (int64_t)kMaxPartialBlocks * ((int64_t)t.d * t.K + 1) * (int64_t)sizeof(double);
+}
+
+int fused_train_step(const float* x, const float* dx, int64_t n, const LibTab& t, const float* w, uint32_t flags,
+                     double* out, void* ws, int64_t ws_bytes, cudaStream_t s) {
+#define X(D, P) \
+  if (t.d == D && t.n_poly == n_poly_terms(D, P)) return run_fused<D, P>(x, dx, n, w, flags, out, ws, ws_bytes, s);
+  SB_FUSED_SHAPES(X)
+#undef X
+  set_error("no fused kernel for d=%d K=%d", t.d, t.K);
+  return SB_ERR_UNSUPPORTED;
+}
+
+}  // namespace sb

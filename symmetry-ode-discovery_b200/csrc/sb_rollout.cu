@@ -1,0 +1,232 @@
+// sb_rollout.cu — lock-step fixed-step integration of dx/dt = Θ(x)·Wᵀ for a batch of initial conditions.
+//
+// Two reference functions share this kernel family:
+//   * `model_utils.py:223-255` odeint(f, x0, t, dt, method, full_traj): torch fp32, Euler or classic RK4,
+//     trajectory WITHOUT x0;
+//   * `data_utils/ode.py:7-28` solve_ode_batch: NumPy float64 RK4 that also records dx = f(x) at every stored
+//     row (row 0 = x0) and makes num_steps-1 updates.
+// One thread integrates one initial condition for all steps: the state, the 4 stage derivatives and the K
+// monomials stay in registers; W sits in the constant bank; the only HBM traffic is the strided trajectory
+// store (and x0). The update formulas reproduce the reference's operation order with explicit
+// round-to-nearest mul/add (no FMA contraction across the reference's separate tensor ops), so that fp32
+// rollouts track torch's and fp64 rollouts track NumPy's to rounding.
+#include "sb_common.cuh"
+
+namespace sb {
+
+namespace {
+
+constexpr int kThreads = 128;
+
+__constant__ double c_rw[kConstW];  // W as float or double (reinterpreted), 16 KB
+
+template <class T> __device__ __forceinline__ T mul_rn(T a, T b);
+template <> __device__ __forceinline__ float mul_rn<float>(float a, float b) { return __fmul_rn(a, b); }
+template <> __device__ __forceinline__ double mul_rn<double>(double a, double b) { return __dmul_rn(a, b); }
+template <class T> __device__ __forceinline__ T add_rn(T a, T b);
+template <> __device__ __forceinline__ float add_rn<float>(float a, float b) { return __fadd_rn(a, b); }
+template <> __device__ __forceinline__ double add_rn<double>(double a, double b) { return __dadd_rn(a, b); }
+template <class T> __device__ __forceinline__ T div_rn(T a, T b);
+template <> __device__ __forceinline__ float div_rn<float>(float a, float b) { return __fdiv_rn(a, b); }
+template <> __device__ __forceinline__ double div_rn<double>(double a, double b) { return __ddiv_rn(a, b); }
+
+// ---- right-hand sides ---------------------------------------------------------------------------
+// specialised: compile-time polynomial library, W from the constant bank
+template <int D, int P, class T>
+struct SpecRhs {
+  static constexpr int DN = D;
+  __device__ __forceinline__ int dim() const { return D; }
+  __device__ __forceinline__ void eval(const T (&x)[D], T (&f)[D]) const {
+    constexpr int K = Poly<D, P>::K;
+    T m[K];
+    expand_poly<D, P>(x, m);
+    const T* w = reinterpret_cast<const T*>(c_rw);
+    static_for<0, D>([&](auto ic) {
+      constexpr int i = ic;
+      // two partial sums (even / odd columns) keep the dependent chain short
+      T s0 = T(0), s1 = T(0);
+      static_for<0, K>([&](auto kc) {
+        constexpr int k = kc;
+        if constexpr (k % 2 == 0) s0 = fma(w[i * K + k], m[k], s0);
+        else s1 = fma(w[i * K + k], m[k], s1);
+      });
+      f[i] = s0 + s1;
+    });
+  }
+};
+
+// generic: runtime table, W from global memory
+template <class T, int KMAX>
+struct GenRhs {
+  static constexpr int DN = SB_MAX_DIM;
+  LibTab t;
+  const T* w;
+  __device__ __forceinline__ int dim() const { return t.d; }
+  __device__ __forceinline__ void eval(const T (&x)[SB_MAX_DIM], T (&f)[SB_MAX_DIM]) const {
+    T m[KMAX];
+    m[0] = T(1);
+    for (int j = 0; j < t.d; ++j) m[1 + j] = x[j];
+    for (int k = 1 + t.d; k < t.n_poly; ++k) m[k] = m[t.parent[k]] * x[t.var[k]];
+    int k = t.n_poly;
+    if (t.sine) for (int j = 0; j < t.d; ++j) m[k++] = sin(x[j]);
+    if (t.exp_) for (int j = 0; j < t.d; ++j) m[k++] = exp(x[j]);
+    for (int i = 0; i < t.d; ++i) {
+      T s = T(0);
+      for (int q = 0; q < t.K; ++q) s = fma(__ldg(w + i * t.K + q), m[q], s);
+      f[i] = s;
+    }
+  }
+};
+
+struct RollArgs {
+  const void* x0;
+  int64_t n_ics;
+  double dt;
+  int64_t n_steps;
+  int64_t stride;
+  int method;
+  int record_dx;
+  void* x_out;
+  void* dx_out;
+  void* x_last;
+};
+
+template <class RHS, class T>
+__device__ __forceinline__ void rollout_body(const RHS& rhs, const RollArgs& a) {
+  constexpr int DN = RHS::DN;
+  const int d = rhs.dim();
+  const int64_t ic = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ic >= a.n_ics) return;
+  const T* x0 = reinterpret_cast<const T*>(a.x0);
+  T* xo = reinterpret_cast<T*>(a.x_out);
+  T* dxo = reinterpret_cast<T*>(a.dx_out);
+  T x[DN], k1[DN], k2[DN], k3[DN], k4[DN], xt[DN];
+#pragma unroll
+  for (int j = 0; j < DN; ++j) x[j] = (j < d) ? x0[ic * d + j] : T(0);
+
+  const T dt = (T)a.dt;
+  const int64_t row_elems = a.n_ics * d;
+  auto store = [&](T* base, int64_t row, const T (&v)[DN]) {
+#pragma unroll
+    for (int j = 0; j < DN; ++j)
+      if (j < d) base[row * row_elems + ic * d + j] = v[j];
+  };
+
+  if (a.record_dx) {
+    // `data_utils/ode.py:14-26`: k_i = dt*f(.), x += (k1 + 2k2 + 2k3 + k4)/6, rows include x0
+    const T half = T(0.5), two = T(2), six = T(6);
+    for (int64_t i = 0; i < a.n_steps; ++i) {
+      rhs.eval(x, k1);
+      if (i % a.stride == 0) {
+        if (xo) store(xo, i / a.stride, x);
+        if (dxo) store(dxo, i / a.stride, k1);
+      }
+      if (i == a.n_steps - 1) break;
+      if (a.method == SB_EULER) {
+#pragma unroll
+        for (int j = 0; j < DN; ++j) x[j] = add_rn(x[j], mul_rn(dt, k1[j]));
+        continue;
+      }
+#pragma unroll
+      for (int j = 0; j < DN; ++j) { k1[j] = mul_rn(dt, k1[j]); xt[j] = add_rn(x[j], mul_rn(half, k1[j])); }
+      rhs.eval(xt, k2);
+#pragma unroll
+      for (int j = 0; j < DN; ++j) { k2[j] = mul_rn(dt, k2[j]); xt[j] = add_rn(x[j], mul_rn(half, k2[j])); }
+      rhs.eval(xt, k3);
+#pragma unroll
+      for (int j = 0; j < DN; ++j) { k3[j] = mul_rn(dt, k3[j]); xt[j] = add_rn(x[j], k3[j]); }
+      rhs.eval(xt, k4);
+#pragma unroll
+      for (int j = 0; j < DN; ++j) {
+        k4[j] = mul_rn(dt, k4[j]);
+        T s = add_rn(k1[j], mul_rn(two, k2[j]));
+        s = add_rn(s, mul_rn(two, k3[j]));
+        s = add_rn(s, k4[j]);
+        x[j] = add_rn(x[j], div_rn(s, six));
+      }
+    }
+  } else {
+    // `model_utils.py:236-253`: x0 + dt/2*k1 etc.; python scalars dt/2, dt/6 are rounded to T once
+    const T hdt = (T)(a.dt / 2.0), sdt = (T)(a.dt / 6.0), two = T(2);
+    for (int64_t s = 1; s <= a.n_steps; ++s) {
+      rhs.eval(x, k1);
+      if (a.method == SB_EULER) {
+#pragma unroll
+        for (int j = 0; j < DN; ++j) x[j] = add_rn(x[j], mul_rn(dt, k1[j]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < DN; ++j) xt[j] = add_rn(x[j], mul_rn(hdt, k1[j]));
+        rhs.eval(xt, k2);
+#pragma unroll
+        for (int j = 0; j < DN; ++j) xt[j] = add_rn(x[j], mul_rn(hdt, k2[j]));
+        rhs.eval(xt, k3);
+#pragma unroll
+        for (int j = 0; j < DN; ++j) xt[j] = add_rn(x[j], mul_rn(dt, k3[j]));
+        rhs.eval(xt, k4);
+#pragma unroll
+        for (int j = 0; j < DN; ++j) {
+          T acc = add_rn(k1[j], mul_rn(two, k2[j]));
+          acc = add_rn(acc, mul_rn(two, k3[j]));
+          acc = add_rn(acc, k4[j]);
+          x[j] = add_rn(x[j], mul_rn(sdt, acc));
+        }
+      }
+      if (xo && s % a.stride == 0) store(xo, s / a.stride - 1, x);
+    }
+  }
+  if (a.x_last) {
+    T* xl = reinterpret_cast<T*>(a.x_last);
+#pragma unroll
+    for (int j = 0; j < DN; ++j)
+      if (j < d) xl[ic * d + j] = x[j];
+  }
+}
+
+template <int D, int P, class T>
+__global__ void __launch_bounds__(kThreads) rollout_spec_kernel(RollArgs a) {
+  SpecRhs<D, P, T> rhs;
+  rollout_body<SpecRhs<D, P, T>, T>(rhs, a);
+}
+
+template <class T, int KMAX>
+__global__ void __launch_bounds__(kThreads) rollout_gen_kernel(LibTab t, const T* w, RollArgs a) {
+  GenRhs<T, KMAX> rhs{t, w};
+  rollout_body<GenRhs<T, KMAX>, T>(rhs, a);
+}
+
+#define SB_ROLL_SHAPES(X) X(2, 2) X(2, 3) X(3, 2) X(3, 3) X(3, 5)
+
+template <class T>
+int launch_rollout(const LibTab& t, const void* w, const RollArgs& a, cudaStream_t s) {
+  const unsigned grid = (unsigned)((a.n_ics + kThreads - 1) / kThreads);
+  if (!t.sine && !t.exp_) {
+#define X(D, P)                                                                                              \
+  if (t.d == D && t.n_poly == n_poly_terms(D, P)) {                                                          \
+    SB_CUDA_TRY(cudaMemcpyToSymbolAsync(c_rw, w, sizeof(T) * D * Poly<D, P>::K, 0, cudaMemcpyDeviceToDevice, s)); \
+    rollout_spec_kernel<D, P, T><<<grid, kThreads, 0, s>>>(a);                                                \
+    SB_LAUNCH_CHECK("rollout_spec_kernel");                                                                  \
+    return SB_OK;                                                                                            \
+  }
+    SB_ROLL_SHAPES(X)
+#undef X
+  }
+  if (t.K <= 16) rollout_gen_kernel<T, 16><<<grid, kThreads, 0, s>>>(t, reinterpret_cast<const T*>(w), a);
+  else if (t.K <= 64) rollout_gen_kernel<T, 64><<<grid, kThreads, 0, s>>>(t, reinterpret_cast<const T*>(w), a);
+  else rollout_gen_kernel<T, 256><<<grid, kThreads, 0, s>>>(t, reinterpret_cast<const T*>(w), a);
+  SB_LAUNCH_CHECK("rollout_gen_kernel");
+  return SB_OK;
+}
+
+}  // namespace
+
+int rollout(const void* x0, int64_t n_ics, const LibTab& t, const void* w, double dt, int64_t n_steps,
+            int64_t stride, int method, int dtype, int record_dx, void* x_out, void* dx_out, void* x_last,
+            cudaStream_t s) {
+  RollArgs a{};
+  a.x0 = x0; a.n_ics = n_ics; a.dt = dt; a.n_steps = n_steps; a.stride = stride; a.method = method;
+  a.record_dx = record_dx; a.x_out = x_out; a.dx_out = dx_out; a.x_last = x_last;
+  if (dtype == SB_F32) return launch_rollout<float>(t, w, a, s);
+  return launch_rollout<double>(t, w, a, s);
+}
+
+}  // namespace sb

@@ -1,0 +1,242 @@
+"""Drop-in replacement for the reference's `model_utils.py`: symmetry-regularisation losses and `odeint`.
+
+The losses keep the reference's signatures and values (`model_utils.py:8-221`). The autoencoder / generator are
+frozen inputs and stay ordinary PyTorch modules; everything that touches the SINDy library — h(x), J_h(x)·u and
+their derivatives — goes through the CUDA operators of `sindy_b200.ops`, which are closed under the
+differentiation the double-vjp `jvp(..., create_graph=True)` trick performs.
+
+`odeint` (`model_utils.py:223-255`) dispatches to the batched rollout kernel whenever no gradient is needed and
+`f` is a SINDyRegression on a CUDA device; otherwise it steps `f` in Python (differentiable, same formulas).
+"""
+from __future__ import annotations
+
+from functools import partial
+
+import torch
+from torch.autograd.functional import jvp
+
+from sindy_b200 import native
+
+__all__ = [
+    "symmreg_i", "symmreg_f", "symmreg_r", "symmreg_r_precomputed", "precompute_symmreg_r", "odeint",
+    "make_symmreg", "make_symmreg_pttrain", "make_symmreg_np", "make_fsymmreg", "make_fsymmreg_pttrain",
+    "make_fsymmreg_np", "make_rsymmreg", "make_rsymmreg_pttrain",
+]
+
+
+def _jvp_fn(require_grad):
+    return partial(jvp, create_graph=True, strict=True) if require_grad else jvp
+
+
+def _centred_latent(autoencoder, x, normalize, z_mean):
+    """z = encode(x) − centre, centre = batch mean ('in_batch') or z_mean / last BatchNorm bias ('global')."""
+    z = autoencoder.encode(x)
+    if normalize == 'in_batch':
+        z = z - z.mean(dim=0, keepdim=True)
+    elif normalize == 'global':
+        if z_mean is None:
+            z_mean = autoencoder.encoder[-2].bias
+        z = z - z_mean
+    return z, z_mean
+
+
+def _act_on_latent(mat, z):
+    """Apply an (n_dims × n_dims) matrix to the flattened latent of every sample, keep z's shape."""
+    flat = z.reshape(z.shape[0], -1)
+    return torch.einsum('jk,...k->...j', mat, flat).reshape(z.shape)
+
+
+def symmreg_i(x_fx, autoencoder, generator, f=None, dfdx=None, normalize='global', z_mean=None, relative=True,
+              require_grad=False, numpy=False):
+    '''
+    Infinitesimal (Lie-derivative) symmetry loss: for every generator v,
+        mean((J_f(x)·v_x − v_fx)²) [/ mean((J_f(x)·v_x)²) if relative],
+    with (v_x, v_fx) = J_decoder(z)·(v z), z = encode([x, f(x)]) − centre.
+    x_fx: (batch, 2, input_dim) input and predicted output; f: map to be symmetrised (or dfdx: its Jacobian).
+    '''
+    if numpy:
+        x_fx = torch.from_numpy(x_fx).float().to(autoencoder.device)
+        if z_mean is not None:
+            z_mean = torch.from_numpy(z_mean).float().to(autoencoder.device)
+        if require_grad:
+            raise ValueError('Cannot require grad when numpy=True.')
+    if f is None and dfdx is None:
+        raise ValueError('Either f or dfdx must be specified.')
+    if f is not None and dfdx is not None:
+        raise ValueError('Only one of f and dfdx can be specified.')
+    jvp_fn = _jvp_fn(require_grad)
+    autoencoder.eval()
+    generator.eval()
+
+    with torch.set_grad_enabled(require_grad):
+        z, _ = _centred_latent(autoencoder, x_fx, normalize, z_mean)
+        x = x_fx[:, 0]
+        loss = 0.0
+        for v in generator.get_full_basis_list():
+            tangent = jvp_fn(autoencoder.decoder, z, v=_act_on_latent(v, z))[1]
+            v_x, v_fx = tangent[:, 0], tangent[:, 1]
+            if f is not None:
+                pushed = jvp_fn(f, x, v_x)[1]
+            else:
+                pushed = torch.einsum('bjk,bk->bj', dfdx, v_x)
+            defect = torch.mean((pushed - v_fx) ** 2)
+            loss += defect / torch.mean(pushed ** 2) if relative else defect
+
+    return loss.cpu().numpy() if numpy else loss
+
+
+def symmreg_f(x_fx, autoencoder, generator, f, normalize='global', z_mean=None, relative=True, require_grad=False,
+              numpy=False):
+    '''Finite-group symmetry loss mean((f(g·x) − g·f(x))²) [/ mean((f(g·x) − f(x))²)] over the deterministic
+    group elements of the generator, transported through the autoencoder (reference `model_utils.py:69-124`).'''
+    autoencoder.eval()
+    generator.eval()
+    if numpy:
+        dev = generator.Li[0].device
+        x_fx = torch.from_numpy(x_fx).float().to(dev)
+        if z_mean is not None:
+            z_mean = torch.from_numpy(z_mean).float().to(dev)
+        if require_grad:
+            raise ValueError('Cannot require grad when numpy=True.')
+
+    with torch.set_grad_enabled(require_grad):
+        z, z_mean = _centred_latent(autoencoder, x_fx, normalize, z_mean)
+        fx = x_fx[:, 1]
+        loss = 0.0
+        for g in generator.get_deterministic_group_elems():
+            moved = autoencoder.decode(_act_on_latent(g, z) + z_mean)
+            g_x, g_fx = moved[:, 0], moved[:, 1]
+            if numpy:
+                f_g_x = torch.from_numpy(f(g_x.cpu().numpy())).float().to(generator.Li[0].device)
+            else:
+                f_g_x = f(g_x)
+            defect = torch.mean((f_g_x - g_fx) ** 2)
+            loss += defect / torch.mean((f_g_x - fx) ** 2) if relative else defect
+
+    return loss.cpu().numpy() if numpy else loss
+
+
+def _group_transform(autoencoder, g, x, normalize='global', z_mean=None):
+    """x -> decode(g·(encode(x) − centre) + centre), first component (reference `model_utils.py:145-158`)."""
+    z, z_mean = _centred_latent(autoencoder, torch.stack([x, x], dim=1), normalize, z_mean)
+    return autoencoder.decode(_act_on_latent(g, z) + z_mean)[:, 0]
+
+
+def symmreg_r(x, autoencoder, generator, h, normalize='global', z_mean=None, require_grad=False, scale=0.01):
+    '''Reversed symmetry loss sum_g mean((J_g(x)·h(x) − h(g(x)))²) (reference `model_utils.py:126-170`).'''
+    jvp_fn = _jvp_fn(require_grad)
+    autoencoder.eval()
+    generator.eval()
+    with torch.set_grad_enabled(require_grad):
+        loss = 0.0
+        for g in generator.get_deterministic_group_elems(scale=scale):
+            move = partial(_group_transform, autoencoder, g, normalize=normalize, z_mean=z_mean)
+            gx = move(x)
+            pushed = jvp_fn(move, x, v=h(x))[1]
+            loss += torch.mean((pushed - h(gx)) ** 2)
+    return loss
+
+
+def symmreg_r_precomputed(x, gx_list, Jgx_list, h):
+    '''symmreg_r with g(x) and J_g(x) from precompute_symmreg_r: a pure streaming loss in the SINDy operators
+    (two library evaluations and one d×d mat-vec per sample and group element).'''
+    loss = 0.0
+    for gx, Jgx in zip(gx_list, Jgx_list):
+        d = x.shape[-1]
+        pushed = torch.einsum('bij,bj->bi', Jgx.reshape(-1, d, d), h(x))  # the reference's Jgx is (B, 1, d, d)
+        loss = loss + torch.mean((pushed - h(gx)) ** 2)
+    return loss
+
+
+def precompute_symmreg_r(x, autoencoder, generator, z_mean=None, scale=0.01):
+    '''g(x) and its Jacobian J_g(x) for every deterministic group element (reference `model_utils.py:172-211`).'''
+    from torch.func import jacfwd, vmap
+
+    autoencoder.eval()
+    generator.eval()
+    gx_list, Jgx_list = [], []
+    with torch.no_grad():
+        for g in generator.get_deterministic_group_elems(scale=scale):
+            move = partial(_group_transform, autoencoder, g, normalize='global', z_mean=z_mean)
+            gx_list.append(move(x))
+            Jgx_list.append(vmap(jacfwd(move))(x))
+    return gx_list, Jgx_list
+
+
+def make_symmreg(autoencoder, generator):
+    return partial(symmreg_i, autoencoder=autoencoder, generator=generator)
+
+
+def make_symmreg_pttrain(autoencoder, generator):
+    return partial(symmreg_i, autoencoder=autoencoder, generator=generator, require_grad=True)
+
+
+def make_symmreg_np(autoencoder, generator):
+    return partial(symmreg_i, autoencoder=autoencoder, generator=generator, numpy=True)
+
+
+def make_fsymmreg(autoencoder, generator):
+    return partial(symmreg_f, autoencoder=autoencoder, generator=generator)
+
+
+def make_fsymmreg_pttrain(autoencoder, generator):
+    return partial(symmreg_f, autoencoder=autoencoder, generator=generator, require_grad=True)
+
+
+def make_fsymmreg_np(autoencoder, generator):
+    return partial(symmreg_f, autoencoder=autoencoder, generator=generator, numpy=True)
+
+
+def make_rsymmreg(autoencoder, generator):
+    return partial(symmreg_r, autoencoder=autoencoder, generator=generator)
+
+
+def make_rsymmreg_pttrain(autoencoder, generator):
+    return partial(symmreg_r, autoencoder=autoencoder, generator=generator, require_grad=True)
+
+
+def _kernel_rollout_ok(f, x0):
+    """The fused rollout applies when f is a SINDyRegression-like module on CUDA and nothing needs a gradient."""
+    if not (hasattr(f, 'library') and hasattr(f, 'mask') and hasattr(f, '_current_Xi')):
+        return False
+    if not (torch.is_tensor(x0) and x0.is_cuda):
+        return False
+    if torch.is_grad_enabled() and (x0.requires_grad or any(p.requires_grad for p in f.parameters())):
+        return False
+    return True
+
+
+def odeint(f, x0, t, dt, method='euler', full_traj=False):
+    '''
+    Integrate dx/dt = f(x) over [0, t] with fixed step dt ('euler' or 'rk4'). n_steps = int(t / dt) as the
+    reference. full_traj: return the (n_steps, ...) stack of states after each step (x0 excluded), else the
+    final state.
+    '''
+    n_steps = int(t / dt)
+    if method not in ('euler', 'rk4'):
+        raise ValueError('Unrecognized ODEInt method.')
+
+    if _kernel_rollout_ok(f, x0):
+        with torch.no_grad():
+            w = (f._current_Xi() * f.mask).detach()
+            traj, _, last = native.rollout(x0, w, f.library, dt, n_steps, stride=1, method=method,
+                                           record_dx=False, want_traj=full_traj, want_last=not full_traj)
+        if full_traj:
+            return traj.view(n_steps, *x0.shape)
+        return last.view(x0.shape)
+
+    def step(x):
+        if method == 'euler':
+            return x + dt * f(x)
+        k1 = f(x)
+        k2 = f(x + dt / 2 * k1)
+        k3 = f(x + dt / 2 * k2)
+        k4 = f(x + dt * k3)
+        return x + dt / 6 * (k1 + 2 * k2 + 2 * k3 + k4)
+
+    traj = []
+    for _ in range(n_steps):
+        x0 = step(x0)
+        if full_traj:
+            traj.append(x0)
+    return torch.stack(traj, dim=0) if full_traj else x0

@@ -1,0 +1,337 @@
+"""Drop-in replacement for the reference's `sindy.py` (SINDyRegression, solve_SINDy*, WSINDyWrapper).
+
+Put this directory in front of the reference on PYTHONPATH: `from sindy import *` then resolves here and
+the reference's `train.py` / `main.py` / `run_configs/*.cfg` work unchanged on a CUDA device. The public
+surface (constructor kwargs, attributes, method names, return values, printed equation format, RNG draw
+order) follows the reference; the tensor arithmetic runs in libsindy_b200.so:
+
+  * Θ(x), h(x)=Θ(x)(Ξ⊙mask)ᵀ and all derivatives autograd asks for -> sindy_b200.ops (reference `sindy.py:79-82,201-203`)
+  * STLSQ (`sindy.py:250-324`): one fused Gram pass (ΘᵀΘ, ΘᵀẊ in fp64) + K×K normal-equation solves instead of
+    a QR of the (N+K)·d × d·K block-diagonal matrix
+  * WSINDy (`sindy.py:332-395`): weak-form integrals VΘ(x), V'x generated on the fly + n_test×K normal equations
+  * the equivariance constraint basis Q (`sindy.py:85-144`) is host-side setup; the symbolic map M is built
+    from exponent arithmetic instead of SymPy.
+
+There is no CPU fallback: calling the model on CPU tensors raises.
+"""
+from __future__ import annotations
+
+import itertools
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from sindy_b200 import native, ops
+from sindy_b200.native import Library
+
+__all__ = ["SINDyRegression", "solve_SINDy_one_step", "solve_SINDy", "WSINDyWrapper"]
+
+
+def _poly_index_tuples(dim: int, order: int):
+    """Index tuples of the polynomial columns: () ; (i) ; (i<=j) ; ... in the reference's column order."""
+    cols = [()]
+    for n in range(1, order + 1):
+        cols.extend(itertools.combinations_with_replacement(range(dim), n))
+    return cols
+
+
+def _lie_derivative_matrix(dim: int, order: int, L: torch.Tensor) -> torch.Tensor:
+    """M with J_Θ(z)·L·z = M·Θ(z) for the polynomial library (reference `sindy.py:123-144`, there via SymPy).
+
+    d/dz_j z^a = a_j z^(a-e_j) and (Lz)_j = sum_l L[j,l] z_l, so row a gets a_j·L[j,l] at column a-e_j+e_l.
+    """
+    cols = _poly_index_tuples(dim, order)
+    where = {c: k for k, c in enumerate(cols)}
+    Lm = np.asarray(L, dtype=np.float64)
+    M = np.zeros((len(cols), len(cols)))
+    for k, c in enumerate(cols):
+        for pos, j in enumerate(c):  # one factor z_j of the monomial at a time (multiplicity = a_j)
+            rest = c[:pos] + c[pos + 1:]
+            for l in range(dim):
+                if Lm[j, l] != 0.0:
+                    M[k, where[tuple(sorted(rest + (l,)))]] += Lm[j, l]
+    return torch.tensor(M, dtype=torch.float32)
+
+
+class SINDyRegression(nn.Module):
+    """Sparse regression dz/dt = Θ(z)·(Ξ⊙mask)ᵀ, optionally with Ξ constrained to be equivariant.
+
+    Arguments (as the reference): latent_dim, poly_order (reference: ≤3; here up to 5), include_sine,
+    include_exp, L_list (Lie algebra generators; non-empty => equivariance-constrained Ξ = reshape(Q·β)),
+    kwargs["threshold"], kwargs["device"], kwargs["constrain_constant"].
+    """
+
+    def __init__(self, latent_dim, poly_order, include_sine, include_exp, L_list=[], **kwargs):
+        super().__init__()
+        device = kwargs["device"]
+        self.latent_dim = latent_dim
+        self.poly_order = poly_order
+        self.L_list = L_list
+        self.constraint = len(L_list) != 0
+        # trigonometric / exponential columns are dropped under the constraint (reference `sindy.py:47-48`)
+        self.include_sine = bool(include_sine) and not self.constraint
+        self.include_exp = bool(include_exp) and not self.constraint
+        self.threshold = kwargs["threshold"]
+        self.library = Library(int(latent_dim), int(poly_order), self.include_sine, self.include_exp)
+
+        if self.constraint:
+            print('Computing equivariance constraint...')
+            self.Q = self.get_Q().to(device)
+            self.beta = nn.Parameter(torch.randn(self.Q.shape[1], device=device))
+            self.const = nn.Parameter(torch.randn(latent_dim, 1, device=device))
+            self.allow_constant = not kwargs['constrain_constant']
+            self.Xi = self.get_Xi()
+        else:
+            self.Xi = nn.Parameter(torch.randn(latent_dim, self.get_term_num(), device=device))
+        self.mask = torch.ones_like(self.Xi, device=device)
+        # kept for API compatibility: names of the column groups
+        self.terms = ['const', 'poly1'] + [f'poly{n}' for n in range(2, poly_order + 1)]
+        if self.include_sine:
+            self.terms.append('sine')
+        if self.include_exp:
+            self.terms.append('exp')
+
+    # ---- library / model -------------------------------------------------------------------------
+    def get_term_num(self):
+        return sum(math.comb(self.latent_dim + n - 1, n) for n in range(self.poly_order + 1)) \
+            + self.latent_dim * (int(self.include_sine) + int(self.include_exp))
+
+    def _current_Xi(self):
+        return self.get_Xi() if self.constraint else self.Xi
+
+    def forward(self, x):
+        self.Xi = self._current_Xi()
+        return ops.sindy_forward(x, self.Xi * self.mask, self.library)
+
+    def eval_Theta_at(self, x):
+        return native.theta(x, self.library)
+
+    def mse_loss(self, x, dx):
+        """mean((forward(x) − dx)²) and its gradient w.r.t. the parameters from ONE pass over the data
+        (the fused train step; same value as `MSELoss()(self(x), dx)`, `train.py:663-664`)."""
+        self.Xi = self._current_Xi()
+        return ops.fused_mse(x, dx, self.Xi * self.mask, self.library)
+
+    # ---- equivariance constraint (host-side setup) -------------------------------------------------
+    def get_M_list(self):
+        return [_lie_derivative_matrix(self.latent_dim, self.poly_order, Li) for Li in self.L_list]
+
+    def get_Q(self):
+        """Null-space basis of the stacked constraint matrices (reference `sindy.py:85-115`)."""
+        blocks = []
+        for M, L in zip(self.get_M_list(), self.L_list):
+            L = torch.as_tensor(L, dtype=torch.float32)
+            if torch.det(L) < 1e-5:  # singular generator: Sylvester form, Ξ stored term-major
+                self.use_kron_product = False
+                Mt = M.transpose(0, 1).contiguous()
+                C = torch.kron(-Mt, torch.eye(L.shape[0])) + torch.kron(torch.eye(Mt.shape[0]), L)
+            else:  # invertible generator: Ξ stored equation-major
+                self.use_kron_product = True
+                C = torch.kron(L.inverse(), M.T)
+                C = C - torch.eye(C.shape[0])
+            blocks.append(C)
+        _, sigma, V = torch.svd(torch.cat(blocks, dim=0))
+        # count trailing singular values below 5e-3; r == 0 keeps the reference's `V[:, -0:]` (= all of V)
+        r = 0
+        for r in range(len(sigma)):
+            if abs(sigma[-1 - r]) > 5e-3:
+                break
+        return V[:, -r:]
+
+    def update_Q(self, new_Li):
+        self.L_list = new_Li
+        self.Q = self.get_Q().to(self.Xi.device)
+        self.beta = nn.Parameter(torch.randn(self.Q.shape[1], device=self.Xi.device))
+
+    def get_Xi(self):
+        flat = self.Q @ self.beta
+        if self.use_kron_product:
+            Xi = flat.view(self.latent_dim, -1)
+        else:
+            Xi = flat.view(-1, self.latent_dim).transpose(0, 1)
+        if self.allow_constant:
+            pad = torch.zeros((Xi.shape[0], Xi.shape[1] - 1), device=Xi.device)
+            Xi += torch.cat([self.const, pad], dim=1)
+        return Xi
+
+    # ---- sparsity mask -----------------------------------------------------------------------------
+    def set_threshold(self, threshold):
+        self.Xi = self._current_Xi()
+        keep = torch.logical_and(torch.abs(self.Xi) > threshold, self.mask)
+        self.mask.data = keep.float()
+
+    def reset_mask(self):
+        self.mask.data = torch.ones_like(self.Xi, device=self.Xi.device)
+
+    # ---- pretty printer ----------------------------------------------------------------------------
+    def term_names(self):
+        names = ['']
+        for c in _poly_index_tuples(self.latent_dim, self.poly_order)[1:]:
+            names.append('*' + '*'.join(f'z{j}' for j in c))
+        if self.include_sine:
+            names += [f'*sin(z{j})' for j in range(self.latent_dim)]
+        if self.include_exp:
+            names += [f'*exp(z{j})' for j in range(self.latent_dim)]
+        return names
+
+    def print(self):
+        Xi = self._current_Xi()
+        names = self.term_names()
+        for i in range(self.latent_dim):
+            line = f'dz{i} ='
+            for k, suffix in enumerate(names):
+                if self.mask[i, k]:
+                    line += f' {Xi[i, k]:.3f}{suffix} +'
+            print(line)
+
+
+# --------------------------------------------------------------------------------------------------------
+# sequentially thresholded least squares on the Gram matrix
+# --------------------------------------------------------------------------------------------------------
+def _min_norm_solve(H: torch.Tensor, rhs: torch.Tensor, rcond: float) -> torch.Tensor:
+    """Minimum-norm solution of the symmetric PSD system H·s = rhs, dropping directions whose singular value
+    in the original least-squares matrix would fall under LAPACK gelsy's rcond·σ_max (eigenvalue < rcond²·λ_max)."""
+    if H.numel() == 0:
+        return rhs.new_zeros(rhs.shape)
+    lam, U = torch.linalg.eigh(H)
+    keep = lam > (rcond * rcond) * lam.max().clamp_min(0)
+    inv = torch.where(keep, 1.0 / lam.clamp_min(torch.finfo(lam.dtype).tiny), torch.zeros_like(lam))
+    return U @ (inv.unsqueeze(-1) * (U.T @ rhs)) if rhs.dim() == 2 else U @ (inv * (U.T @ rhs))
+
+
+def _stlsq_update(regressor, G, b, ridge, n_rows, st_threshold):
+    """Shared tail of solve_SINDy_one_step / WSINDyWrapper.solve: solve on the current support, write the
+    parameters back, threshold, report convergence. G (K×K) and b (K×d) are fp64 normal-equation blocks;
+    `ridge` is what is added to G's diagonal; n_rows is the row count of the reference's least-squares matrix
+    (only used for the rank tolerance)."""
+    d, K = regressor.latent_dim, G.shape[0]
+    dev = G.device
+    H = G + ridge * torch.eye(K, dtype=G.dtype, device=dev)
+    mask = regressor.mask > 0.0
+    rcond = float(torch.finfo(torch.float32).eps) * max(n_rows, K)
+    prev_mask = regressor.mask.clone()
+
+    if bool(torch.all(mask)) and not regressor.constraint:
+        sol = _min_norm_solve(H, b, rcond)                       # K×d
+        regressor.Xi.data = sol.T.to(torch.float32).contiguous()
+    else:
+        flat_mask = mask.flatten()                               # equation-major: i*K + k
+        idx = torch.nonzero(flat_mask, as_tuple=False).flatten()
+        eq, col = idx // K, idx % K
+        # (I_d ⊗ H)[m, m]: zero between different equations
+        Hm = H[col][:, col] * (eq.unsqueeze(1) == eq.unsqueeze(0)).to(H.dtype)
+        rhs = b.T.reshape(-1)[idx]
+        if regressor.constraint:
+            Q = regressor.Q.to(torch.float64)
+            if regressor.allow_constant:
+                extra = torch.zeros((Q.shape[0], d), dtype=Q.dtype, device=dev)
+                for i in range(d):
+                    extra[i * Q.shape[0] // d, i] = 1.0
+                Q = torch.cat([Q, extra], dim=1)
+            Qm = Q[idx]
+            effective = torch.any(Qm != 0.0, dim=0)              # drop parameters that touch no live column
+            Qe = Qm[:, effective]
+            sol = _min_norm_solve(Qe.T @ Hm @ Qe, Qe.T @ rhs, rcond)
+            full = torch.zeros(Q.shape[1], dtype=torch.float64, device=dev)
+            full[effective] = sol
+            full = full.to(torch.float32)
+            if regressor.allow_constant:
+                regressor.beta.data = full[:-d].contiguous()
+                regressor.const.data = full[-d:].view(-1, 1).contiguous()
+            else:
+                regressor.beta.data = full
+        else:
+            sol = _min_norm_solve(Hm, rhs, rcond)
+            coef = torch.zeros(d * K, dtype=torch.float32, device=dev)
+            coef[idx] = sol.to(torch.float32)
+            regressor.Xi.data = coef.view(d, K)
+    regressor.set_threshold(st_threshold)
+    return torch.allclose(prev_mask, regressor.mask)
+
+
+def solve_SINDy_one_step(regressor, x, y, w_sindy_reg, st_threshold, **kwargs):
+    '''
+    One STLSQ step: argmin_w ||y - Θ(x) w||² + w_sindy_reg²·||w||² on the current support (the reference stacks
+    w_sindy_reg·I under Θ, `sindy.py:262`, hence the square), then threshold.
+
+    x & y: (n_samples, dim). Returns (mean squared residual / n_samples, converged) like the reference's
+    `residuals.mean() / x.shape[0]`; the residual is computed from the normal equations (the reference's LAPACK
+    driver returns an empty `residuals`, i.e. NaN, for this shape).
+    '''
+    lib = regressor.library
+    flags = native.SB_STEP_GRAM | native.SB_STEP_B
+    with torch.no_grad():
+        out = native.train_step(x, y, None, lib, flags)
+        parts = native.unpack_step(out, lib, flags)
+        G, b = parts["gram"], parts["b"]
+        n = x.reshape(-1, lib.dim).shape[0]
+        converged = _stlsq_update(regressor, G, b, float(w_sindy_reg) ** 2, n + lib.K, st_threshold)
+        # residual of the augmented system with the parameters just written (before masking by the new mask)
+        Xi = regressor._current_Xi().to(torch.float64)
+        yy = (y.reshape(-1, lib.dim).double() ** 2).sum(0)
+        quad = torch.einsum('ik,kl,il->i', Xi, G, Xi) - 2.0 * torch.einsum('ik,ki->i', Xi, b) + yy
+        quad = quad + float(w_sindy_reg) ** 2 * (Xi ** 2).sum(1)
+        residual = (quad.mean() / n).to(torch.float32)
+    return residual, converged
+
+
+def solve_SINDy(regressor, x, y, w_sindy_reg, st_threshold, max_iter=5, **kwargs):
+    regressor.reset_mask()
+    residual = None
+    for _ in range(max_iter):
+        residual, converged = solve_SINDy_one_step(regressor, x, y, w_sindy_reg, st_threshold)
+        if converged:
+            break
+    return residual
+
+
+class WSINDyWrapper():
+    """Weak SINDy as a regularised least-squares problem (reference `sindy.py:327-395`).
+
+    Test functions g_k(t) = sqrt(2/T)·sin(kπt/T), k = 1..num_test_funcs. `t` must be the uniform grid
+    t_i = i·dt starting at 0 that `main_wsindy.py:41` builds.
+    """
+
+    def __init__(self, regressor, t, t_max, num_test_funcs=50, test_func_family='trig', device='cuda', **kwargs):
+        if test_func_family != 'trig':
+            raise NotImplementedError(f'test_func_family={test_func_family} not implemented')
+        self.t = t.to(device)
+        self.dt = self.t[1] - self.t[0]
+        self.t_max = float(t_max)
+        self.num_test_funcs = int(num_test_funcs)
+        self.regressor = regressor
+        # dense V only to form the n_test×n_test weight M = V·Vᵀ once (the reference multiplies by Vᵀ on the
+        # left of both sides, `sindy.py:369-370`); the data-dependent integrals never read V.
+        k = torch.arange(1, num_test_funcs + 1, dtype=torch.float32, device=device).view(-1, 1)
+        phase = k * torch.pi * self.t / t_max
+        amp = math.sqrt(2 / t_max)
+        self.V = self.dt * (amp * torch.sin(phase))
+        self.V_drv = self.dt * (amp * k * np.pi / t_max * torch.cos(phase))
+        self.M = self.V.double() @ self.V.double().T
+
+    def integrals(self, x):
+        """G = V·Θ(x) (n_test×K) and b = −V'·x (n_test×d), fp64, from the fused kernel."""
+        return native.wsindy_integrals(x, self.regressor.library, float(self.dt), self.t_max, self.num_test_funcs)
+
+    def solve(self, x, w_sindy_reg, st_threshold, **kwargs):
+        '''
+        x: (seq_len, dim) on the wrapper's uniform grid. Solves [VᵀG; sqrt(w)·I] ξ = [Vᵀb; 0] on the current
+        support through its normal equations (GᵀMG + w·I) ξ = GᵀM b, then thresholds.
+        Returns (mean squared residual of that system, converged).
+        '''
+        with torch.no_grad():
+            if x.shape[0] != self.t.shape[0]:
+                raise ValueError(f'x has {x.shape[0]} time samples, the wrapper was built for {self.t.shape[0]}')
+            Gw, bw = self.integrals(x)
+            MG = self.M @ Gw
+            A = Gw.T @ MG                                        # K×K
+            rhs = MG.T @ bw                                      # K×d
+            K = A.shape[0]
+            converged = _stlsq_update(self.regressor, A, rhs, float(w_sindy_reg), x.shape[0] + K, st_threshold)
+            Xi = self.regressor._current_Xi().to(torch.float64)
+            bb = torch.einsum('ji,jl,li->i', bw, self.M, bw)
+            quad = torch.einsum('ik,kl,il->i', Xi, A, Xi) - 2.0 * torch.einsum('ik,ki->i', Xi, rhs) + bb
+            quad = quad + float(w_sindy_reg) * (Xi ** 2).sum(1)
+        return quad.mean().item(), converged

@@ -1,0 +1,417 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on seeded inputs and against the golden
+fixtures produced by the unmodified reference. Tolerances follow BASELINE.json's north_star: identical sparsity
+pattern, coefficients 1e-4 relative (fp32), RK4 trajectories 1e-5 relative; tighter where the arithmetic allows."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import sindy_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+LIBS = [(2, 2, 0, 0), (2, 2, 0, 1), (2, 3, 0, 0), (2, 3, 1, 0), (3, 3, 1, 1), (3, 2, 0, 0), (1, 3, 1, 1), (4, 3, 0, 0)]
+EXT_LIBS = [(3, 5, 0, 0), (3, 3, 0, 0), (2, 5, 1, 0), (3, 4, 0, 1), (5, 2, 0, 0), (8, 2, 1, 1), (6, 3, 0, 0)]
+
+
+@pytest.fixture(scope="module")
+def nat():
+    from sindy_b200 import native
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    native.load()
+    return native
+
+
+def dev(a, dtype=torch.float32):
+    return torch.as_tensor(np.asarray(a), dtype=dtype).cuda()
+
+
+def rel(a, b):
+    a = a.detach().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
+    b = b.detach().cpu().numpy() if torch.is_tensor(b) else np.asarray(b)
+    a, b = a.astype(np.float64), b.astype(np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# a1-a4: library, forward, loss, gradient
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("d,p,s,e", LIBS)
+def test_golden_theta_forward_step(nat, golden, d, p, s, e):
+    g = golden("model")
+    t = f"d{d}p{p}s{s}e{e}"
+    lib = nat.Library(d, p, bool(s), bool(e))
+    x, dx, Xi, mask = dev(g[t + "_x"]), dev(g[t + "_dx"]), dev(g[t + "_Xi"]), dev(g[t + "_mask"])
+    assert lib.K == Xi.shape[1]
+    th = nat.theta(x, lib).cpu().numpy()
+    npoly = O.term_count(d, p)
+    assert np.array_equal(th[:, :npoly], g[t + "_theta"][:, :npoly])          # bit-exact monomials
+    np.testing.assert_allclose(th, g[t + "_theta"], rtol=5e-7, atol=1e-7)       # sin/exp: <= 2 ulp
+    W = Xi * mask
+    assert rel(nat.forward(x, W, lib), g[t + "_y"]) < 2e-6
+    assert rel(nat.forward(x[:64].reshape(32, 2, d), W, lib), g[t + "_y3"]) < 2e-6
+    flags = nat.SB_STEP_LOSS | nat.SB_STEP_GRAD
+    parts = nat.unpack_step(nat.train_step(x, dx, W, lib, flags), lib, flags)
+    n = x.shape[0]
+    assert float(parts["n"]) == n
+    loss = float(parts["sum_sq"]) / (n * d)
+    assert abs(loss - float(g[t + "_loss_x"])) < 3e-6 * float(g[t + "_loss_x"])
+    grad = (2.0 / (n * d)) * parts["grad_raw"].cpu().numpy() * g[t + "_mask"] + 0.01 * np.sign(g[t + "_Xi"])
+    assert rel(grad, g[t + "_grad"]) < 1e-5
+
+
+@pytest.mark.parametrize("d,p,s,e", LIBS + EXT_LIBS)
+@pytest.mark.parametrize("n", [1, 3, 1000, 4099])
+def test_train_step_all_sections_vs_oracle(nat, d, p, s, e, n):
+    rng = np.random.default_rng(d * 100 + p * 10 + n)
+    lib = nat.Library(d, p, bool(s), bool(e))
+    K = lib.K
+    assert K == O.term_count(d, p, s, e)
+    x = rng.uniform(-1, 1, (n, d)).astype(np.float32)
+    dx = rng.standard_normal((n, d)).astype(np.float32)
+    W = (rng.standard_normal((d, K)) * (rng.random((d, K)) > 0.3)).astype(np.float32)
+    ref = O.train_step_sums(x, dx, W, p, s, e)
+    for flags in (nat.SB_STEP_LOSS | nat.SB_STEP_GRAD, nat.SB_STEP_GRAM | nat.SB_STEP_B, 15, nat.SB_STEP_LOSS,
+                  nat.SB_STEP_GRAM, nat.SB_STEP_GRAD | nat.SB_STEP_B):
+        parts = nat.unpack_step(nat.train_step(dev(x), dev(dx), dev(W), lib, flags), lib, flags)
+        assert float(parts["n"]) == n
+        scale = max(ref["sum_sq"], 1e-30)
+        if flags & (nat.SB_STEP_LOSS | nat.SB_STEP_GRAD):
+            assert abs(float(parts["sum_sq"]) - ref["sum_sq"]) < 2e-5 * scale
+        for key in ("grad_raw", "gram", "b"):
+            if key in parts:
+                assert rel(parts[key], ref[key]) < 2e-5, (key, flags)
+
+
+def test_train_step_empty_and_errors(nat):
+    lib = nat.Library(2, 2)
+    x = torch.empty(0, 2, device="cuda")
+    flags = nat.SB_STEP_LOSS | nat.SB_STEP_GRAD
+    out = nat.train_step(x, x.clone(), torch.zeros(2, 6, device="cuda"), lib, flags)
+    assert torch.all(out == 0)
+    with pytest.raises(nat.SindyB200Error):
+        nat.Library(9, 2).K
+    with pytest.raises(nat.SindyB200Error):
+        nat.Library(2, 6).K
+    with pytest.raises(RuntimeError):
+        nat.forward(torch.zeros(4, 2), torch.zeros(2, 6), lib)           # CPU tensor: no fallback
+    with pytest.raises(ValueError):
+        nat.forward(torch.zeros(4, 3, device="cuda"), torch.zeros(2, 6, device="cuda"), lib)
+
+
+def test_train_step_misaligned_and_ragged_inputs_take_the_same_values(nat):
+    # a view that starts 12 bytes into an allocation is not TMA-aligned: must fall back to the generic kernel
+    rng = np.random.default_rng(1)
+    lib = nat.Library(3, 5)
+    n = 5003
+    xb, dxb = dev(rng.uniform(-1, 1, (n + 1, 3))), dev(rng.standard_normal((n + 1, 3)))
+    W = dev(rng.standard_normal((3, 56)))
+    flags = nat.SB_STEP_LOSS | nat.SB_STEP_GRAD
+    a = nat.train_step(xb[1:], dxb[1:], W, lib, flags)
+    b = nat.train_step(xb[1:].clone(), dxb[1:].clone(), W, lib, flags)
+    assert rel(a, b) < 1e-5
+    # determinism: bitwise identical on repeat
+    c = nat.train_step(xb[1:].clone(), dxb[1:].clone(), W, lib, flags)
+    assert torch.equal(b, c)
+
+
+def test_train_step_linearity_large(nat):
+    # size-independent property at a size the oracle cannot reach: the residual sums are affine in W, and the
+    # Gram-free identity  grad(W) = grad(0) + W·G  ties the fused kernel to the generic Gram kernel.
+    lib = nat.Library(3, 5)
+    n = 3_000_017
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.rand(n, 3, device="cuda", generator=gen) * 2 - 1
+    dx = torch.randn(n, 3, device="cuda", generator=gen)
+    W = torch.randn(3, 56, device="cuda", generator=gen)
+    f = nat.SB_STEP_LOSS | nat.SB_STEP_GRAD
+    assert nat.train_step_variant(lib, f).startswith("fused_tma<3,5>")
+    g0 = nat.unpack_step(nat.train_step(x, dx, torch.zeros_like(W), lib, f), lib, f)
+    g1 = nat.unpack_step(nat.train_step(x, dx, W, lib, f), lib, f)
+    g2 = nat.unpack_step(nat.train_step(x, dx, 2 * W, lib, f), lib, f)
+    lin = g1["grad_raw"] - g0["grad_raw"]
+    assert rel(g2["grad_raw"] - g0["grad_raw"], 2 * lin) < 2e-5
+    fb = nat.SB_STEP_GRAM | nat.SB_STEP_B
+    gb = nat.unpack_step(nat.train_step(x, dx, None, lib, fb), lib, fb)
+    assert rel(g0["grad_raw"], -gb["b"].T) < 2e-5
+    assert rel(lin, W.double() @ gb["gram"]) < 5e-5
+    # sum r^2 = tr(W G W^T) - 2 tr(W b) + sum dx^2
+    quad = torch.einsum('ik,kl,il->', W.double(), gb["gram"], W.double()) - 2 * (W.double() * gb["b"].T).sum() \
+        + (dx.double() ** 2).sum()
+    assert abs(float(g1["sum_sq"]) - float(quad)) < 2e-5 * float(quad)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# derivatives: backward, jvp, jvp-backward; autograd closure incl. the double-vjp trick
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("d,p,s,e", LIBS + EXT_LIBS[:4])
+def test_derivative_kernels_vs_oracle(nat, d, p, s, e):
+    rng = np.random.default_rng(d * 7 + p)
+    lib = nat.Library(d, p, bool(s), bool(e))
+    K, n = lib.K, 777
+    x = rng.uniform(-1, 1, (n, d)).astype(np.float32)
+    u = rng.standard_normal((n, d)).astype(np.float32)
+    g = rng.standard_normal((n, d)).astype(np.float32)
+    W = rng.standard_normal((d, K)).astype(np.float32)
+    gw, gx = nat.backward(dev(x), dev(g), dev(W), lib, True, True)
+    rw, rx = O.backward(x, g, W, p, s, e)
+    assert rel(gw, rw) < 1e-5 and rel(gx, rx) < 1e-5
+    assert rel(nat.jvp(dev(x), dev(u), dev(W), lib), O.jvp(x, u, W, p, s, e)) < 1e-5
+    tw, tx, tu = nat.jvp_backward(dev(x), dev(u), dev(g), dev(W), lib)
+    ow, ox, ou = O.jvp_backward(x, u, g, W, p, s, e)
+    assert rel(tw, ow) < 1e-5 and rel(tx, ox) < 1e-5 and rel(tu, ou) < 1e-5
+
+
+@pytest.mark.parametrize("d,p,s,e", [(2, 2, 0, 1), (2, 3, 1, 0), (3, 3, 0, 0), (3, 2, 1, 1)])
+def test_golden_jvp_and_double_backward(nat, golden, d, p, s, e):
+    import sindy
+    from torch.autograd.functional import jvp
+    g = golden("jvp")
+    t = f"d{d}p{p}s{s}e{e}"
+    reg = sindy.SINDyRegression(d, p, bool(s), bool(e), threshold=0.05, device="cuda", constrain_constant=True)
+    reg.Xi.data = dev(g[t + "_Xi"])
+    x, u = dev(g[t + "_x"]), dev(g[t + "_u"])
+    assert rel(jvp(reg, x, u)[1], g[t + "_jv"]) < 1e-5
+
+    def two_steps(z):
+        z1 = z + 0.1 * reg(z)
+        return z1 + 0.1 * reg(z1)
+
+    jv2 = jvp(two_steps, x, u, create_graph=True, strict=True)[1]
+    loss = torch.mean((jv2 - dev(g[t + "_tgt"])) ** 2) / torch.mean(jv2 ** 2)
+    reg.zero_grad()
+    loss.backward()
+    assert abs(float(loss) - float(g[t + "_loss_two"])) < 1e-5 * abs(float(g[t + "_loss_two"]))
+    assert rel(reg.Xi.grad, g[t + "_grad_two"]) < 1e-4
+    gens = dev(g[t + "_gens"])
+    lie = 0.0
+    for v in gens:
+        lie = lie + torch.norm(jvp(reg, x, torch.einsum('ij,bj->bi', v, x), create_graph=True)[1]
+                               - torch.einsum('ij,bj->bi', v, reg(x))) ** 2
+    reg.zero_grad()
+    lie.backward()
+    assert abs(float(lie) - float(g[t + "_lie"])) < 1e-5 * float(g[t + "_lie"])
+    assert rel(reg.Xi.grad, g[t + "_grad_lie"]) < 1e-4
+
+
+def test_closure_matches_reference_autograd(nat, golden):
+    """The LBFGS closure of train.py:645-690 written against the drop-in module, both the 3-pass autograd form
+    and the fused one-pass form."""
+    import sindy
+    g = golden("model")
+    for (d, p, s, e) in LIBS:
+        t = f"d{d}p{p}s{s}e{e}"
+        reg = sindy.SINDyRegression(d, p, bool(s), bool(e), threshold=0.05, device="cuda", constrain_constant=True)
+        reg.Xi.data = dev(g[t + "_Xi"])
+        reg.mask.data = dev(g[t + "_mask"])
+        x, dx = dev(g[t + "_x"]), dev(g[t + "_dx"])
+        for fused in (False, True):
+            reg.zero_grad()
+            loss_x = reg.mse_loss(x, dx) if fused else torch.nn.MSELoss()(reg(x), dx)
+            l1 = sum(torch.norm(q, 1) for q in reg.parameters())
+            (loss_x + 0.01 * l1).backward()
+            assert abs(float(loss_x) - float(g[t + "_loss_x"])) < 3e-6 * float(g[t + "_loss_x"])
+            assert rel(reg.Xi.grad, g[t + "_grad"]) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------------
+# a9/a13: STLSQ and the equivariance constraint
+# ---------------------------------------------------------------------------------------------------------
+def test_golden_stlsq(nat, golden):
+    import sindy
+    g = golden("stlsq")
+    x, y = dev(g["selkov_x"]), dev(g["selkov_y"])
+    for w in (0.0, 0.3):
+        tag = f"selkov_w{int(w * 10)}"
+        reg = sindy.SINDyRegression(2, 3, False, False, threshold=0.05, device="cuda", constrain_constant=True)
+        reg.reset_mask()
+        steps = g[tag + "_masks"].shape[0]
+        for it in range(steps):
+            _, conv = sindy.solve_SINDy_one_step(reg, x, y, w, 0.05)
+            assert np.array_equal(reg.mask.cpu().numpy(), g[tag + "_masks"][it])
+            assert rel(reg.Xi, g[tag + "_xis"][it]) < 1e-4
+        assert conv
+    reg = sindy.SINDyRegression(3, 3, False, False, threshold=0.1, device="cuda", constrain_constant=True)
+    sindy.solve_SINDy(reg, dev(g["lorenz_x"]), dev(g["lorenz_y"]), 0.0, 0.1)
+    assert np.array_equal(reg.mask.cpu().numpy(), g["lorenz_mask"])
+    assert rel(reg.Xi, g["lorenz_Xi"]) < 1e-4
+
+
+def test_golden_constrained_stlsq(nat, golden):
+    import sindy
+    g = golden("stlsq")
+    so2 = torch.tensor([[0.0, 1.0], [-1.0, 0.0]])
+    sc2 = torch.diag(torch.tensor([2.0, 1.0]))
+    for name, L, xk, yk in (("dosc_so2", so2, "dosc_x", "dosc_y"), ("growth_sc2", sc2, "growth_x", "growth_y")):
+        for cc in (True, False):
+            tag = f"{name}_cc{int(cc)}"
+            reg = sindy.SINDyRegression(2, 2, False, False, L_list=[L], threshold=0.05, device="cuda",
+                                        constrain_constant=cc)
+            steps = g[tag + "_masks"].shape[0]
+            for it in range(steps):
+                sindy.solve_SINDy_one_step(reg, dev(g[xk]), dev(g[yk]), 0.0, 0.05)
+                assert np.array_equal(reg.mask.cpu().numpy(), g[tag + "_masks"][it]), (tag, it)
+                assert rel(reg.get_Xi(), g[tag + "_xis"][it]) < 2e-4, (tag, it)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# a10: WSINDy
+# ---------------------------------------------------------------------------------------------------------
+def test_golden_wsindy(nat, golden):
+    import sindy
+    g = golden("wsindy")
+    traj, dt, t_max = dev(g["traj"]), float(g["dt"]), float(g["t_max"])
+    T = traj.shape[0]
+    t = torch.arange(T) * dt
+    reg = sindy.SINDyRegression(2, 3, False, False, threshold=0.075, device="cuda", constrain_constant=True)
+    wr = sindy.WSINDyWrapper(reg, t, t_max, device="cuda")
+    assert np.array_equal(wr.V[:, ::40].cpu().numpy(), g["V"]) or rel(wr.V[:, ::40], g["V"]) < 1e-6
+    G, b = wr.integrals(traj)
+    assert rel(G, g["G"]) < 1e-5 and rel(b, g["b"]) < 1e-5
+    Go, bo = O.wsindy_integrals(g["traj"], dt, t_max, 3)
+    assert rel(G, Go) < 1e-5 and rel(b, bo) < 1e-5
+    for w in (0.05, 0.01):
+        tag = f"w{int(w * 100)}"
+        reg = sindy.SINDyRegression(2, 3, False, False, threshold=0.075, device="cuda", constrain_constant=True)
+        wr = sindy.WSINDyWrapper(reg, t, t_max, device="cuda")
+        for it in range(g[tag + "_masks"].shape[0]):
+            _, conv = wr.solve(traj, w, 0.075)
+            assert np.array_equal(reg.mask.cpu().numpy(), g[tag + "_masks"][it]), (w, it)
+            assert rel(reg.Xi, g[tag + "_xis"][it]) < 5e-4, (w, it)
+        assert conv
+    # batched integrals over trajectories == one at a time
+    trajs = dev(g["trajs3"])
+    Gb, bb = nat.wsindy_integrals(trajs, reg.library, dt, t_max, 50)
+    G0, b0 = nat.wsindy_integrals(trajs[1], reg.library, dt, t_max, 50)
+    assert torch.equal(Gb[1], G0) and torch.equal(bb[1], b0)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# a11/a12: rollouts
+# ---------------------------------------------------------------------------------------------------------
+def test_golden_solve_ode_batch(nat, golden):
+    from data_utils import ode, systems
+    g = golden("rollout")
+    for name in ("dosc", "growth", "lv", "selkov"):
+        f = systems.SYSTEMS[name]()
+        x, dx = ode.solve_ode_batch(f, g[name + "_x0"], dt=0.002, num_steps=301)
+        assert x.shape == (301, 7, 2) and x.dtype == np.float64
+        assert rel(x[::10], g[name + "_x"]) < 1e-11 and rel(dx[::10], g[name + "_dx"]) < 1e-11
+    x, dx = ode.solve_ode_batch(systems.dosc(), g["dosc_long_x0"], dt=0.002, num_steps=10000)
+    assert rel(x[::500], g["dosc_long_x"]) < 1e-10 and rel(dx[::500], g["dosc_long_dx"]) < 1e-10
+    # fp32 state over the longest config (10^4 steps): north_star tolerance 1e-5 relative
+    lib = nat.Library(2, 2)
+    xo, _, _ = nat.rollout(dev(g["dosc_long_x0"]), dev(systems.dosc().Xi), lib, 0.002, 10000, 500, "rk4",
+                           record_dx=True)
+    assert rel(xo, g["dosc_long_x"]) < 1e-5
+    with pytest.raises(TypeError):
+        ode.solve_ode_batch(lambda x: -x, g["dosc_x0"])
+
+
+def test_golden_odeint(nat, golden):
+    import sindy
+    import model_utils
+    g = golden("rollout")
+    truth = golden("model")
+    for name, (p, e) in {"selkov": (3, False), "lv": (2, True)}.items():
+        reg = sindy.SINDyRegression(2, p, False, e, threshold=0.05, device="cuda", constrain_constant=True)
+        reg.Xi.data = dev(truth["truth_" + name])
+        x0 = dev(g[name + "_x0"])
+        with torch.no_grad():
+            tr = model_utils.odeint(reg, x0, 1.0, 0.002, method='rk4', full_traj=True)
+            eu = model_utils.odeint(reg, x0, 0.1, 0.01, method='euler')
+        assert tr.shape == (500, 7, 2)
+        assert rel(tr[::25], g[name + "_odeint_rk4"]) < 1e-5 and rel(eu, g[name + "_odeint_euler"]) < 1e-5
+        # differentiable python stepping path gives the same states as the fused rollout
+        tr2 = model_utils.odeint(reg, x0, 0.1, 0.002, method='rk4', full_traj=True)
+        assert tr2.requires_grad and rel(tr2.detach(), tr[:50]) < 1e-6
+    reg = sindy.SINDyRegression(3, 3, False, False, threshold=0.05, device="cuda", constrain_constant=True)
+    reg.Xi.data = dev(g["rand3_Xi"])
+    with torch.no_grad():
+        tr = model_utils.odeint(reg, dev(g["rand3_x0"]), 0.5, 0.01, method='rk4', full_traj=True)
+    assert rel(tr, g["rand3_odeint_rk4"]) < 1e-5
+    with pytest.raises(ValueError):
+        model_utils.odeint(reg, dev(g["rand3_x0"]), 0.5, 0.01, method='heun')
+
+
+@pytest.mark.parametrize("d,p,s,e", [(3, 5, 0, 0), (2, 3, 1, 1), (4, 2, 0, 0)])
+def test_rollout_generic_and_specialised_vs_oracle(nat, d, p, s, e):
+    rng = np.random.default_rng(3)
+    lib = nat.Library(d, p, bool(s), bool(e))
+    Xi = (0.2 * rng.standard_normal((d, lib.K)) * (rng.random((d, lib.K)) > 0.5))
+    x0 = rng.uniform(-0.5, 0.5, (33, d))
+    x, dx = O.solve_ode_batch(O.library_rhs(Xi, p, s, e), x0, dt=0.01, num_steps=101)
+    xo, dxo, xl = nat.rollout(dev(x0, torch.float64), dev(Xi, torch.float64), lib, 0.01, 101, 10, "rk4", record_dx=True)
+    assert rel(xo, x[::10]) < 1e-11 and rel(dxo, dx[::10]) < 1e-11 and rel(xl, x[-1]) < 1e-11
+    tr = O.odeint(O.library_rhs(Xi.astype(np.float32), p, s, e), x0.astype(np.float32), 1.0, 0.01, 'rk4', True)
+    xo, _, xl = nat.rollout(dev(x0), dev(Xi), lib, 0.01, 100, 4, "rk4")
+    assert xo.shape[0] == 25 and rel(xo, tr[3::4]) < 1e-5 and rel(xl, tr[-1]) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------------
+# a6/a7/a8: symmetry regularisers with frozen stand-ins
+# ---------------------------------------------------------------------------------------------------------
+def test_golden_symmreg(nat, golden):
+    import sindy
+    import model_utils
+    import standins
+    g = golden("symmreg")
+    sd = {k[3:]: torch.as_tensor(g[k]) for k in g.keys() if k.startswith("ae_")}
+    ae, gen = standins.make_standins(seed=0, input_dim=2, n_comps=2, hidden=32, state_dict=sd, device="cuda")
+    assert rel(torch.stack(gen.get_full_basis_list()), g["gen_basis"]) == 0
+    x = dev(g["x"])
+    for (p, e, tag) in [(2, True, "lv"), (3, False, "cubic")]:
+        reg = sindy.SINDyRegression(2, p, False, e, threshold=0.05, device="cuda", constrain_constant=True)
+        reg.Xi.data = dev(g[tag + "_Xi"])
+
+        def forward_step(z):
+            return model_utils.odeint(reg, z, 0.1, 0.01)
+
+        x_fx = torch.stack([x, forward_step(x)], dim=1)
+        li = model_utils.symmreg_i(x_fx, ae, gen, f=forward_step, require_grad=True)
+        reg.zero_grad(); li.backward()
+        assert abs(float(li) - float(g[tag + "_li"])) < 1e-4 * float(g[tag + "_li"])
+        assert rel(reg.Xi.grad, g[tag + "_gi"]) < 5e-4
+        lr = model_utils.symmreg_r(x, ae, gen, h=reg, require_grad=True)
+        reg.zero_grad(); lr.backward()
+        assert abs(float(lr) - float(g[tag + "_lr"])) < 1e-4 * float(g[tag + "_lr"])
+        assert rel(reg.Xi.grad, g[tag + "_gr"]) < 5e-4
+        x_fx = torch.stack([x, forward_step(x)], dim=1)
+        lf = model_utils.symmreg_f(x_fx, ae, gen, f=forward_step, require_grad=True)
+        reg.zero_grad(); lf.backward()
+        assert abs(float(lf) - float(g[tag + "_lf"])) < 2e-4 * float(g[tag + "_lf"])
+        assert rel(reg.Xi.grad, g[tag + "_gf"]) < 1e-3
+        # precomputed form: streaming loss in the SINDy operators only
+        reg.zero_grad()
+        lp = model_utils.symmreg_r_precomputed(x, list(dev(g[tag + "_gx"])), list(dev(g[tag + "_Jgx"])), reg)
+        lp.backward()
+        assert abs(float(lp) - float(g[tag + "_lr"])) < 1e-4 * float(g[tag + "_lr"])
+        assert rel(reg.Xi.grad, g[tag + "_gr"]) < 5e-4
+        gx_list, Jgx_list = model_utils.precompute_symmreg_r(x, ae, gen)
+        assert rel(torch.stack(gx_list), g[tag + "_gx"]) < 1e-5
+        assert rel(torch.stack(Jgx_list), g[tag + "_Jgx_ref"]) < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------------------
+# a3 end to end: LBFGS fit reaches the reference's equations
+# ---------------------------------------------------------------------------------------------------------
+def test_golden_lbfgs_fit(nat, golden):
+    import sindy
+    import train
+    g = golden("lbfgs")
+    x, dx = dev(g["x"]), dev(g["dx"])
+    loader = [(x, dx)]
+    so2 = torch.tensor([[0.0, 1.0], [-1.0, 0.0]])
+    for tag, L_list in (("sindy", []), ("esindy", [so2])):
+        reg = sindy.SINDyRegression(2, 2, False, False, L_list=L_list, threshold=0.05, device="cuda",
+                                    constrain_constant=True)
+        for k in [k for k in g.keys() if k.startswith(tag + "_init_")]:
+            getattr(reg, k[len(tag) + 6:]).data = dev(g[k])
+        train.train_SIGED_lbfgs(
+            train_loader=loader, test_loader=loader, num_epochs=200, device="cuda", log_interval=1000,
+            save_interval=100000, save_dir=None, autoencoder=torch.nn.Identity(), generator=torch.nn.Identity(),
+            regressor=reg, regressor_dst=None, use_latent=False, distill_latent=False, lr_sindy=0.1, w_sindy_z=0.0,
+            w_sindy_x=1.0, sindy_reg_type='l1', w_sindy_reg=0.0, sym_reg_type='i', w_sym_reg=0.0, st_freq=50,
+            threshold=0.05, int_t=0.1, int_dt=0.01, print_eq=False)
+        Xi = reg.get_Xi() if reg.constraint else reg.Xi
+        assert np.array_equal(reg.mask.cpu().numpy(), g[tag + "_mask"]), tag
+        assert rel(Xi * reg.mask, g[tag + "_Xi"] * g[tag + "_mask"]) < 1e-3, tag
