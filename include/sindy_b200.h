@@ -77,6 +77,9 @@ typedef struct {
 int sb_version(void);
 const char* sb_last_error(void);
 
+/* Number of kernels this library has launched in this process (all threads, all devices). */
+unsigned long long sb_kernel_launches(void);
+
 /* Number of CUDA devices visible (0 if none / driver missing). */
 int sb_device_count(void);
 

@@ -1,5 +1,6 @@
 // sb_api.cu — the extern "C" surface declared in include/sindy_b200.h: argument validation,
 // library-table construction and dispatch between the specialised and the generic kernels.
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -9,6 +10,9 @@
 namespace sb {
 
 static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -65,6 +69,8 @@ extern "C" {
 int sb_version(void) { return 100; }
 
 const char* sb_last_error(void) { return g_err; }
+
+unsigned long long sb_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int sb_device_count(void) {
   int n = 0;

@@ -27,10 +27,13 @@ int cuda_fail(cudaError_t e, const char* what);
     if (_e != cudaSuccess) return ::sb::cuda_fail(_e, #expr);     \
   } while (0)
 
+// every kernel launch of the library goes through this check; it also feeds sb_kernel_launches()
+void count_launch();
 #define SB_LAUNCH_CHECK(name)                                     \
   do {                                                            \
     cudaError_t _e = cudaGetLastError();                          \
     if (_e != cudaSuccess) return ::sb::cuda_fail(_e, name);      \
+    ::sb::count_launch();                                         \
   } while (0)
 
 // ---------------------------------------------------------------------------------------------

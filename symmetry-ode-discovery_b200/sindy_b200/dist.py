@@ -1,0 +1,151 @@
+"""Sample-sharded train step: one process per GPU, each rank owns its trajectories, ONE all-reduce per step.
+
+The reference is single-device (`parser_utils.py:118`); the shard/all-reduce layer is new. Every rank runs the
+fused kernel over its own samples and obtains the packed fp64 SUMS `[Σr², n, Σ r_iΘ_k (d×K), (Gram), (ΘᵀẊ)]`
+(see include/sindy_b200.h). Sums — not per-rank means — are all-reduced, then every rank divides by the GLOBAL
+n·d, so the loss/gradient equal the single-process values for any (uneven) sharding and Ξ / mask / optimiser
+state stay replicated without further communication. The message is d·K+2 doubles (1.4 KB for d=3, K=56):
+latency-bound, so the whole step (W upload, kernel, all-reduce, epilogue) is captured in a CUDA graph.
+
+`HostStreamedStep` is the host-buffer entry point: x/dx live in pinned host memory and are streamed through
+two device staging buffers on two copy streams while the kernel consumes the previous chunk.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import native
+from .native import Library
+
+
+def _world(group) -> int:
+    return dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+
+
+def mse_from_sums(packed: torch.Tensor, lib: Library, w: torch.Tensor, mask: Optional[torch.Tensor] = None,
+                  w_l1: float = 0.0, params_l1: Optional[torch.Tensor] = None):
+    """Epilogue on the (all-reduced) packed sums: loss = Σr²/(n·d) [+ w_l1·‖Ξ‖₁] and dL/dΞ
+    (`train.py:663-664,680-683,689`). `w` is only used for its dtype/shape; `params_l1` (default: none) is the
+    unmasked parameter tensor of the L1 term."""
+    d, K = lib.dim, lib.K
+    denom = packed[1] * d
+    loss = packed[0] / denom
+    grad = packed[2:2 + d * K].view(d, K) * (2.0 / denom)
+    if mask is not None:
+        grad = grad * mask
+    if w_l1 != 0.0 and params_l1 is not None:
+        loss = loss + w_l1 * params_l1.abs().sum()
+        grad = grad + w_l1 * torch.sign(params_l1)
+    return loss, grad.to(w.dtype)
+
+
+class ShardedTrainStep:
+    """loss, grad = step(W) over samples sharded across the ranks of `group` (or a single process).
+
+    local_sums: callable (W) -> packed fp64 sums of THIS rank's shard. The default runs the CUDA kernel on
+    (x, dx); tests inject a CPU stand-in to exercise the combine logic with the gloo backend.
+    """
+
+    def __init__(self, lib: Library, x: Optional[torch.Tensor] = None, dx: Optional[torch.Tensor] = None,
+                 flags: int = native.SB_STEP_LOSS | native.SB_STEP_GRAD, group=None,
+                 local_sums: Optional[Callable[[torch.Tensor], torch.Tensor]] = None, use_graph: bool = False):
+        self.lib, self.flags, self.group = lib, flags, group
+        self.x, self.dx = x, dx
+        self._custom = local_sums
+        self._out = None
+        self._graph = None
+        self._use_graph = use_graph and local_sums is None
+        self._static_w = None
+        self._static_res = None
+
+    # -- pieces ----------------------------------------------------------------------------------------
+    def local_sums(self, w: torch.Tensor) -> torch.Tensor:
+        if self._custom is not None:
+            return self._custom(w)
+        if self._out is None:
+            self._out = torch.empty(self.lib.step_out_len(self.flags), dtype=torch.float64, device=self.x.device)
+        return native.train_step(self.x, self.dx, w, self.lib, self.flags, out=self._out)
+
+    def reduced_sums(self, w: torch.Tensor) -> torch.Tensor:
+        packed = self.local_sums(w)
+        if _world(self.group) > 1:
+            dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=self.group)
+        return packed
+
+    def _eager(self, w, mask, w_l1, params_l1):
+        wm = w if mask is None else w * mask
+        packed = self.reduced_sums(wm)
+        return mse_from_sums(packed, self.lib, w, mask, w_l1, params_l1)
+
+    # -- public ----------------------------------------------------------------------------------------
+    def step(self, w: torch.Tensor, mask: Optional[torch.Tensor] = None, w_l1: float = 0.0):
+        """One closure evaluation: (loss, dL/dΞ) with Ξ = w (unmasked parameters) and optional mask."""
+        if not self._use_graph:
+            return self._eager(w, mask, w_l1, w if w_l1 != 0.0 else None)
+        if self._graph is None:
+            self._static_w = w.detach().clone()
+            self._static_mask = None if mask is None else mask.detach().clone()
+            # warm-up on a side stream (allocations, NCCL channel setup) before capture
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(3):
+                    self._eager(self._static_w, self._static_mask, w_l1, self._static_w if w_l1 else None)
+            torch.cuda.current_stream().wait_stream(s)
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self._static_res = self._eager(self._static_w, self._static_mask, w_l1,
+                                               self._static_w if w_l1 else None)
+        self._static_w.copy_(w)
+        if mask is not None:
+            self._static_mask.copy_(mask)
+        self._graph.replay()
+        return self._static_res
+
+
+class HostStreamedStep:
+    """Fused train step over (x, dx) that live in PINNED HOST memory: chunks are copied host->device on two
+    alternating streams into two staging buffers and reduced by the kernel as they land; the packed sums of the
+    chunks are added on the device. The timed region of bench.py's `e2e` is exactly one `__call__`."""
+
+    def __init__(self, lib: Library, chunk_samples: int = 1 << 22, device: Optional[torch.device] = None,
+                 flags: int = native.SB_STEP_LOSS | native.SB_STEP_GRAD):
+        self.lib, self.flags = lib, flags
+        self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        self.chunk = int(chunk_samples)
+        d = lib.dim
+        self._bufs = [(torch.empty(self.chunk, d, dtype=torch.float32, device=self.dev),
+                       torch.empty(self.chunk, d, dtype=torch.float32, device=self.dev)) for _ in range(2)]
+        self._streams = [torch.cuda.Stream(self.dev) for _ in range(2)]
+        n_out = lib.step_out_len(flags)
+        self._outs = [torch.empty(n_out, dtype=torch.float64, device=self.dev) for _ in range(2)]
+        self._accs = [torch.zeros(n_out, dtype=torch.float64, device=self.dev) for _ in range(2)]  # one per stream
+        self.h2d_bytes = 0
+
+    def __call__(self, x_host: torch.Tensor, dx_host: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+        if x_host.is_cuda or dx_host.is_cuda:
+            raise ValueError("HostStreamedStep takes host tensors (pinned for asynchronous copies)")
+        n = x_host.shape[0]
+        main = torch.cuda.current_stream(self.dev)
+        self.h2d_bytes = 0
+        for s, acc in zip(self._streams, self._accs):
+            s.wait_stream(main)
+            with torch.cuda.stream(s):
+                acc.zero_()
+        for ci, start in enumerate(range(0, n, self.chunk)):
+            stop = min(start + self.chunk, n)
+            m = stop - start
+            slot = ci % 2
+            bx, bdx = self._bufs[slot]
+            with torch.cuda.stream(self._streams[slot]):
+                bx[:m].copy_(x_host[start:stop], non_blocking=True)
+                bdx[:m].copy_(dx_host[start:stop], non_blocking=True)
+                native.train_step(bx[:m], bdx[:m], w, self.lib, self.flags, out=self._outs[slot])
+                self._accs[slot] += self._outs[slot]
+            self.h2d_bytes += 2 * m * self.lib.dim * 4
+        for s in self._streams:
+            main.wait_stream(s)
+        return self._accs[0] + self._accs[1]

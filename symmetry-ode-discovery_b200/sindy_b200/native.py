@@ -34,6 +34,7 @@ _SIGNATURES = {
     "sb_version": (c_int, []),
     "sb_last_error": (c_char_p, []),
     "sb_device_count": (c_int, []),
+    "sb_kernel_launches": (ctypes.c_ulonglong, []),
     "sb_library_size": (c_int, [POINTER(_CLibrary)]),
     "sb_library_exponents": (c_int, [POINTER(_CLibrary), POINTER(c_int32)]),
     "sb_workspace_bytes": (c_int64, [POINTER(_CLibrary)]),
@@ -127,6 +128,11 @@ class Library:
 
 def device_count() -> int:
     return int(load().sb_device_count())
+
+
+def kernel_launches() -> int:
+    """Kernels launched by libsindy_b200.so in this process so far."""
+    return int(load().sb_kernel_launches())
 
 
 # ---------------------------------------------------------------------------------------------------------

@@ -1,0 +1,183 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol include/sindy_b200.h declares, the host-side
+library enumeration matches the oracle, and the host logic of the drop-in modules (constraint basis, STLSQ update
+on normal equations, thresholding) reproduces the reference goldens when fed oracle-computed sums.
+No compute entry point is called (no GPU here)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import sindy_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from sindy_b200 import native
+    header = open(os.path.join(ROOT, "include", "sindy_b200.h")).read()
+    declared = set(re.findall(r"\b(sb_[a-z0-9_]+)\s*\(", header))
+    declared -= {"sb_status", "sb_library"}
+    lib = native.load()
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert declared == set(native.EXPORTED_SYMBOLS)
+    assert lib.sb_version() >= 100
+
+
+@pytest.mark.parametrize("d,p,s,e", [(2, 2, 0, 0), (2, 3, 1, 1), (3, 5, 0, 0), (4, 3, 0, 1), (8, 2, 1, 1), (1, 5, 0, 0)])
+def test_library_size_and_exponents(d, p, s, e):
+    from sindy_b200 import native
+    lib = native.Library(d, p, bool(s), bool(e))
+    assert lib.K == O.term_count(d, p, s, e)
+    E = lib.exponents().numpy()
+    npoly = O.term_count(d, p)
+    assert np.array_equal(E[:npoly], O.exponents(d, p))
+    if s:
+        assert np.array_equal(E[npoly:npoly + d], -np.eye(d, dtype=np.int32))
+    assert lib.workspace_bytes() > 0 and lib.step_out_len(15) == 2 + d * lib.K + lib.K ** 2 + lib.K * d
+
+
+def test_unsupported_libraries_are_rejected_loudly():
+    from sindy_b200 import native
+    for bad in (native.Library(0, 2), native.Library(9, 2), native.Library(2, 0), native.Library(2, 6),
+                native.Library(8, 4)):
+        with pytest.raises(native.SindyB200Error):
+            bad.K
+    with pytest.raises(RuntimeError):   # CPU tensors never reach a kernel
+        native.forward(torch.zeros(3, 2), torch.zeros(2, 6), native.Library(2, 2))
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from sindy_b200 import native
+    monkeypatch.setattr(native, "_lib", None)
+    monkeypatch.setattr(native, "LIB_PATH", "/nonexistent/libsindy_b200.so")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        native.load()
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "symmetry-ode-discovery_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.replace("oracle/", "").lower() or "import" not in text.lower() or \
+                    not re.search(r"^\s*(from|import)\s+oracle", text, re.M), f
+
+
+def test_constraint_basis_matches_reference(golden):
+    import sindy
+    g = golden("stlsq")
+    so2 = torch.tensor([[0.0, 1.0], [-1.0, 0.0]])
+    sc2 = torch.diag(torch.tensor([2.0, 1.0]))
+    for name, L in (("so2", so2), ("scaling2", sc2)):
+        torch.manual_seed(0)
+        reg = sindy.SINDyRegression(2, 2, False, False, L_list=[L], threshold=0.05, device="cpu", constrain_constant=True)
+        np.testing.assert_allclose(reg.get_M_list()[0].numpy(), g[name + "_M"], atol=1e-6)
+        assert int(reg.use_kron_product) == int(g[name + "_kron"])
+        # same SVD routine on the same matrix: identical basis, hence identical Ξ from the same RNG draws
+        np.testing.assert_allclose(reg.Q.numpy(), g[name + "_Q"], atol=1e-6)
+        np.testing.assert_allclose(reg.beta.detach().numpy(), g[name + "_beta0"], atol=0)
+        np.testing.assert_allclose(reg.const.detach().numpy(), g[name + "_const0"], atol=0)
+        np.testing.assert_allclose(reg.get_Xi().detach().numpy(), g[name + "_Xi0"], atol=1e-6)
+    L3 = torch.tensor([[0.0, 1.0, 0.0], [-1.0, 0.0, 0.0], [0.0, 0.0, 0.0]])
+    reg = sindy.SINDyRegression(3, 2, False, False, L_list=[L3], threshold=0.05, device="cpu", constrain_constant=True)
+    assert int(reg.use_kron_product) == int(g["sing3_kron"]) == 0
+    np.testing.assert_allclose(reg.get_M_list()[0].numpy(), g["sing3_M"], atol=1e-6)
+    # null spaces agree (bases may differ by an orthogonal mix when singular values are degenerate)
+    Qr, Qo = g["sing3_Q"], reg.Q.numpy()
+    assert Qr.shape == Qo.shape
+    np.testing.assert_allclose(Qr @ Qr.T, Qo @ Qo.T, atol=1e-4)
+
+
+def test_threshold_and_printer(golden, capsys):
+    import sindy
+    reg = sindy.SINDyRegression(2, 1, False, False, threshold=0.05, device="cpu", constrain_constant=True)
+    reg.Xi.data = torch.tensor([[0.05, 0.0500001, -0.05], [1.0, -1.0, 0.0]])
+    reg.set_threshold(0.05)
+    assert np.array_equal(reg.mask.numpy(), golden("model")["ka_threshold_mask"])
+    reg.print()
+    out = capsys.readouterr().out.splitlines()
+    assert out == ["dz0 = 0.050*z0 +", "dz1 = 1.000 + -1.000*z0 +"]
+    reg = sindy.SINDyRegression(2, 3, True, True, threshold=0.05, device="cpu", constrain_constant=True)
+    assert reg.get_term_num() == 14 == reg.Xi.shape[1]
+    assert reg.term_names()[8] == "*z0*z1*z1" and reg.term_names()[-1] == "*exp(z1)"
+    assert "Xi" in reg.state_dict() and "mask" not in reg.state_dict()
+
+
+def _feed_stlsq(reg, x, y, w, thr, p):
+    """solve_SINDy_one_step's host logic with the Gram sums supplied by the oracle instead of the kernel."""
+    import sindy
+    s = O.train_step_sums(x, y, np.zeros((y.shape[1], O.term_count(x.shape[1], p))), p)
+    G, b = torch.from_numpy(s["gram"]), torch.from_numpy(s["b"])
+    return sindy._stlsq_update(reg, G, b, float(w) ** 2, x.shape[0] + G.shape[0], thr)
+
+
+def test_stlsq_host_logic_reproduces_reference(golden):
+    import sindy
+    g = golden("stlsq")
+    for w in (0.0, 0.3):
+        tag = f"selkov_w{int(w * 10)}"
+        reg = sindy.SINDyRegression(2, 3, False, False, threshold=0.05, device="cpu", constrain_constant=True)
+        reg.reset_mask()
+        for it in range(g[tag + "_masks"].shape[0]):
+            conv = _feed_stlsq(reg, g["selkov_x"], g["selkov_y"], w, 0.05, 3)
+            assert np.array_equal(reg.mask.numpy(), g[tag + "_masks"][it])
+            np.testing.assert_allclose(reg.Xi.detach().numpy(), g[tag + "_xis"][it], rtol=0, atol=1e-4 * np.abs(g[tag + "_xis"][it]).max())
+        assert conv
+    so2 = torch.tensor([[0.0, 1.0], [-1.0, 0.0]])
+    sc2 = torch.diag(torch.tensor([2.0, 1.0]))
+    for name, L, xk, yk in (("dosc_so2", so2, "dosc_x", "dosc_y"), ("growth_sc2", sc2, "growth_x", "growth_y")):
+        for cc in (True, False):
+            tag = f"{name}_cc{int(cc)}"
+            torch.manual_seed(0)
+            reg = sindy.SINDyRegression(2, 2, False, False, L_list=[L], threshold=0.05, device="cpu", constrain_constant=cc)
+            for it in range(g[tag + "_masks"].shape[0]):
+                _feed_stlsq(reg, g[xk], g[yk], 0.0, 0.05, 2)
+                assert np.array_equal(reg.mask.numpy(), g[tag + "_masks"][it]), (tag, it)
+                ref = g[tag + "_xis"][it]
+                np.testing.assert_allclose(reg.get_Xi().detach().numpy(), ref, rtol=0, atol=2e-4 * np.abs(ref).max())
+
+
+def test_wsindy_host_logic_reproduces_reference(golden):
+    import sindy
+    g = golden("wsindy")
+    traj, dt, t_max = g["traj"], float(g["dt"]), float(g["t_max"])
+    T = traj.shape[0]
+    t = torch.arange(T) * dt
+    Go, bo = O.wsindy_integrals(traj, dt, t_max, 3)
+    for w in (0.05, 0.01):
+        tag = f"w{int(w * 100)}"
+        reg = sindy.SINDyRegression(2, 3, False, False, threshold=0.075, device="cpu", constrain_constant=True)
+        wr = sindy.WSINDyWrapper(reg, t, t_max, device="cpu")
+        assert np.array_equal(wr.V[:, ::40].numpy(), g["V"]) and np.array_equal(wr.V_drv[:, ::40].numpy(), g["V_drv"])
+        wr.integrals = lambda x: (torch.from_numpy(Go), torch.from_numpy(bo))   # oracle instead of the kernel
+        for it in range(g[tag + "_masks"].shape[0]):
+            _, conv = wr.solve(torch.from_numpy(traj), w, 0.075)
+            assert np.array_equal(reg.mask.numpy(), g[tag + "_masks"][it]), (w, it)
+            ref = g[tag + "_xis"][it]
+            np.testing.assert_allclose(reg.Xi.detach().numpy(), ref, rtol=0, atol=5e-4 * np.abs(ref).max())
+        assert conv
+
+
+def test_odeint_python_path_and_errors():
+    import model_utils
+    f = lambda x: -x
+    x0 = torch.ones(4, 2)
+    out = model_utils.odeint(f, x0, 0.3, 0.1, method='euler')           # int(0.3/0.1) == 2 steps
+    assert torch.allclose(out, torch.full((4, 2), 0.81))
+    tr = model_utils.odeint(f, x0, 1.0, 0.1, method='rk4', full_traj=True)
+    assert tr.shape == (10, 4, 2) and abs(float(tr[-1, 0, 0]) - np.exp(-1.0)) < 1e-6
+    with pytest.raises(ValueError):
+        model_utils.odeint(f, x0, 1.0, 0.1, method='midpoint')
+
+
+def test_systems_match_truth_tables(golden):
+    from data_utils import systems
+    g = golden("model")
+    for name in ("dosc", "growth", "lv", "selkov"):
+        assert np.allclose(systems.SYSTEMS[name]().Xi, g["truth_" + name])

@@ -1,0 +1,76 @@
+"""world_size-2 gloo test of the sample-sharded step: uneven shards, one all-reduce of packed SUMS, global mean.
+The CUDA kernel is replaced by the CPU oracle through ShardedTrainStep's `local_sums` hook (test infrastructure
+only); what is under test is the host-side combine logic that runs identically over NCCL."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, ret):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "symmetry-ode-discovery_b200")]
+    from oracle import sindy_oracle as O
+    from sindy_b200 import native
+    from sindy_b200.dist import ShardedTrainStep
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    d, p = 2, 3
+    lib = native.Library(d, p)
+    rng = np.random.default_rng(0)
+    n = 1001
+    x = rng.uniform(-1, 1, (n, d)).astype(np.float32)
+    dx = rng.standard_normal((n, d)).astype(np.float32)
+    W = rng.standard_normal((d, lib.K)).astype(np.float32)
+    mask = (rng.random((d, lib.K)) > 0.3).astype(np.float32)
+    cut = 313                                      # uneven shards: 313 and 688 samples
+    lo, hi = (0, cut) if rank == 0 else (cut, n)
+
+    def local_sums(w):
+        s = O.train_step_sums(x[lo:hi], dx[lo:hi], w.numpy(), p)
+        return torch.from_numpy(np.concatenate([[s["sum_sq"], s["n"]], s["grad_raw"].ravel()]))
+
+    step = ShardedTrainStep(lib, local_sums=local_sums)
+    loss, grad = step.step(torch.from_numpy(W), torch.from_numpy(mask), w_l1=0.01)
+    ref_loss, ref_grad = O.mse_loss_and_grad(x, dx, W * mask, p)
+    ref_loss += 0.01 * np.abs(W).sum()
+    ref_grad = ref_grad * mask + 0.01 * np.sign(W)
+    ok = abs(float(loss) - ref_loss) < 1e-10 * abs(ref_loss) and np.allclose(grad.numpy(), ref_grad, rtol=1e-5, atol=1e-7)
+    # every rank holds the identical result (replicated optimiser state stays in sync)
+    both = [torch.zeros_like(grad) for _ in range(world)]
+    dist.all_gather(both, grad)
+    ok = ok and torch.equal(both[0], both[1])
+    ret[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_sharded_step_two_ranks_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    port = 29500 + (os.getpid() % 500)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, ret)) for r in range(world)]
+    for q in procs:
+        q.start()
+    for q in procs:
+        q.join(timeout=120)
+        assert q.exitcode == 0
+    assert ret.get(0) and ret.get(1)
+
+
+def test_single_process_step_matches_formula():
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "symmetry-ode-discovery_b200")]
+    from sindy_b200 import native
+    from sindy_b200.dist import mse_from_sums
+    lib = native.Library(2, 2)
+    packed = torch.arange(2 + 12, dtype=torch.float64) + 1.0
+    packed[1] = 50.0
+    w = torch.ones(2, 6)
+    loss, grad = mse_from_sums(packed, lib, w)
+    assert abs(float(loss) - 1.0 / 100.0) < 1e-15
+    assert torch.allclose(grad.double(), packed[2:].view(2, 6) * (2.0 / 100.0))
