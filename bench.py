@@ -329,10 +329,11 @@ def main():
     del xh, dxh
 
     if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
-        return
+        # every collective of this run has completed on all ranks (the last one is the e2e all-reduce); leave
+        # without NCCL teardown: destroy_process_group() after CUDA-graph capture of collectives was seen to hang
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(0)
 
     # ---- roofline (rank 0) ----
     peaks, peak_src = measured_peaks()
@@ -382,9 +383,10 @@ def main():
         if not args.skip_extras:
             result["extra"] = extras(native, dev, peaks, fp32_peak)
     print(json.dumps(result))
+    sys.stdout.flush()
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        os._exit(0)
 
 
 def extras(native, dev, peaks, fp32_peak):
