@@ -219,31 +219,33 @@ def main():
     flags = native.SB_STEP_LOSS | native.SB_STEP_GRAD
     variant = native.train_step_variant(lib, flags)
 
+    # One step = one closure evaluation + the parameter update, all on the device:
+    #   1 GPU : pack Ξ⊙mask -> fused kernel (its last block writes loss and dL/dΞ, L1 term included) -> Ξ -= lr·grad
+    #   N GPUs: the same with an all-reduce of the packed sums and a 1-launch epilogue, replayed as ONE CUDA graph
     use_graph = (world > 1) and not args.no_graph
-    stepper = ShardedTrainStep(lib, x, dx, flags=flags, use_graph=use_graph)
-    Xi = Xi0.clone()
+    stepper = ShardedTrainStep(lib, x, dx, flags=flags, use_graph=use_graph, sgd_lr=1e-3)
+    stepper.step(Xi0, mask, w_l1)  # loads the static parameters (and captures the graph when enabled)
+    stepper.xi.copy_(Xi0)
     kern_events = []
 
     def one_step(record=False):
-        nonlocal Xi
-        if use_graph:
-            loss, grad = stepper.step(Xi, mask)
-        else:
-            wm = Xi * mask
-            if record:
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-            packed = stepper.local_sums(wm)
-            if record:
+        if record and not use_graph:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            packed, loss_t, grad_t = stepper._buffers(dev)
+            if world == 1:
+                native.closure(x, dx, stepper.xi, stepper.mask, lib, w_l1, packed=packed, loss=loss_t, grad=grad_t)
                 e1.record()
-                kern_events.append((e0, e1))
-            if world > 1:
+            else:
+                native.train_step(x, dx, stepper.xi * stepper.mask, lib, flags, out=packed)
+                e1.record()
                 dist.all_reduce(packed)
-            loss, grad = mse_from_sums(packed, lib, Xi, mask)
-        l1 = Xi.abs().sum()          # evaluated even at weight 0 (`train.py:680-683`)
-        loss = loss + w_l1 * l1
-        Xi = Xi - 1e-3 * grad        # parameter update: the next step sees new coefficients
-        return loss
+                native.step_epilogue(packed, stepper.xi, stepper.mask, lib, w_l1, loss=loss_t, grad=grad_t)
+            kern_events.append((e0, e1))
+            stepper.xi.add_(grad_t, alpha=-1e-3)
+            return loss_t
+        loss_t, _ = stepper.step(None, None, w_l1)
+        return loss_t
 
     def barrier():
         if world > 1:
@@ -268,7 +270,7 @@ def main():
     clocks = sampler.stop() if sampler else None
     launches = native.kernel_launches() - launches0
     if use_graph:
-        launches = args.steps  # one fused kernel per replayed step (launched by the graph, not via the ABI)
+        launches = 3 * args.steps  # per replayed step: pack_w + fused kernel + epilogue (launched by the graph)
     elapsed_ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
     if world > 1:
         dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
@@ -279,10 +281,10 @@ def main():
     # ---- kernel-only duration (roofline numerator) ----
     if kern_events:
         kern_ms = sum(a.elapsed_time(b) for a, b in kern_events) / len(kern_events)
-        kern_how = "CUDA events around the kernel launch inside every timed step"
+        kern_how = "CUDA events around the library call (pack_w + fused kernel) inside every timed step"
     else:
         out = torch.empty(lib.step_out_len(flags), dtype=torch.float64, device=dev)
-        wm = Xi * mask
+        wm = stepper.xi * mask
         native.train_step(x, dx, wm, lib, flags, out=out)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

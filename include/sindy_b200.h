@@ -130,6 +130,21 @@ int sb_train_step(const float* x, const float* dx, int64_t n, const sb_library* 
                   const float* w, uint32_t flags, double* out, void* workspace,
                   int64_t workspace_bytes, void* stream);
 
+/* One closure evaluation of the LBFGS / Adam loops without sym-reg (`train.py:645-690`, `:512-527`):
+ *   loss = mean((Θ(x)(Ξ⊙mask)ᵀ − dx)²) + w_l1·‖Ξ‖₁      (fp32 scalar, device)
+ *   grad = dloss/dΞ = (2/(n·d))·(Σ_n r⊗Θ)⊙mask + w_l1·sign(Ξ)   (fp32 d×K, device)
+ * xi is the UNMASKED parameter matrix, mask (d×K fp32, may be NULL) the sparsity mask. packed_out (2+d·K doubles,
+ * required) also receives the raw sums of sb_train_step(LOSS|GRAD). For the specialised libraries this is two
+ * launches: Ξ⊙mask into the constant bank, then the fused kernel whose last block writes loss and grad. */
+int sb_closure(const float* x, const float* dx, int64_t n, const sb_library* lib, const float* xi,
+               const float* mask, double w_l1, double* packed_out, float* loss_out, float* grad_out,
+               void* workspace, int64_t workspace_bytes, void* stream);
+
+/* The same epilogue applied to packed sums that were combined across GPUs (all-reduce(sum) of
+ * sb_train_step's output): loss_out / grad_out as in sb_closure (either may be NULL). */
+int sb_step_epilogue(const double* packed, const sb_library* lib, const float* xi, const float* mask,
+                     double w_l1, float* loss_out, float* grad_out, void* stream);
+
 /* Name of the kernel variant sb_train_step would dispatch for this library ("fused_tma<3,5>",
  * "generic" ...). Static string. */
 const char* sb_train_step_variant(const sb_library* lib, uint32_t flags);

@@ -192,8 +192,40 @@ int sb_train_step(const float* x, const float* dx, int64_t n, const sb_library* 
   // the TMA-staged kernels need 16-byte aligned, contiguous x / dx
   const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dx)) & 15u) == 0;
   if (n > 0 && aligned && fused_supported(t, flags))
-    return fused_train_step(x, dx, n, t, w, flags, out, ws, ws_bytes, (cudaStream_t)stream);
+    return fused_train_step(x, dx, n, t, w, nullptr, flags, out, nullptr, ws, ws_bytes, (cudaStream_t)stream);
   return generic_train_step(x, dx, n, t, w, flags, out, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int sb_closure(const float* x, const float* dx, int64_t n, const sb_library* lib, const float* xi, const float* mask,
+               double w_l1, double* packed_out, float* loss_out, float* grad_out, void* ws, int64_t ws_bytes,
+               void* stream) {
+  LibTab t;
+  SB_TRY(build_table(lib, &t));
+  const uint32_t flags = SB_STEP_LOSS | SB_STEP_GRAD;
+  SB_TRY(step_args_ok(x, dx, n, xi, flags, packed_out, ws));
+  SB_TRY(check_ptr(loss_out, "loss_out")); SB_TRY(check_ptr(grad_out, "grad_out"));
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dx)) & 15u) == 0;
+  if (n > 0 && aligned && fused_supported(t, flags)) {
+    ClosureOut co{w_l1, loss_out, grad_out};
+    return fused_train_step(x, dx, n, t, xi, mask, flags, packed_out, &co, ws, ws_bytes, s);
+  }
+  // generic path: W = Ξ⊙mask in the workspace tail, residual rows, then the epilogue launch
+  const int64_t need = generic_workspace_bytes(t);
+  if (ws_bytes < need) { set_error("workspace too small: %lld < %lld bytes", (long long)ws_bytes, (long long)need); return SB_ERR_WORKSPACE; }
+  float* wm = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + need - (int64_t)t.d * t.K * (int64_t)sizeof(float));
+  SB_TRY(mask_mul(xi, mask, wm, t.d * t.K, s));
+  SB_TRY(generic_train_step(x, dx, n, t, wm, flags, packed_out, ws, ws_bytes, s));
+  return step_epilogue(packed_out, t, xi, mask, w_l1, loss_out, grad_out, s);
+}
+
+int sb_step_epilogue(const double* packed, const sb_library* lib, const float* xi, const float* mask, double w_l1,
+                     float* loss_out, float* grad_out, void* stream) {
+  LibTab t;
+  SB_TRY(build_table(lib, &t));
+  SB_TRY(check_ptr(packed, "packed")); SB_TRY(check_ptr(xi, "xi"));
+  if (!loss_out && !grad_out) return SB_OK;
+  return step_epilogue(packed, t, xi, mask, w_l1, loss_out, grad_out, (cudaStream_t)stream);
 }
 
 const char* sb_train_step_variant(const sb_library* lib, uint32_t flags) {

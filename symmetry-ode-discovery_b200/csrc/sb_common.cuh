@@ -168,11 +168,25 @@ int generic_train_step(const float* x, const float* dx, int64_t n, const LibTab&
                        uint32_t flags, double* out, void* ws, int64_t ws_bytes, cudaStream_t s);
 int64_t generic_workspace_bytes(const LibTab& t);
 
-// specialised (compile-time library, register-resident, TMA-staged) fused train step
+// closure epilogue outputs (loss fp32 scalar, dL/dXi fp32 d×K) and the L1 weight
+struct ClosureOut {
+  double w_l1;
+  float* loss;
+  float* grad;
+};
+// loss / gradient from (all-reduced) packed sums; one tiny launch
+int step_epilogue(const double* packed, const LibTab& t, const float* xi, const float* mask, double w_l1,
+                  float* loss_out, float* grad_out, cudaStream_t s);
+// W = xi ⊙ mask into `dst` (d×K floats)
+int mask_mul(const float* xi, const float* mask, float* dst, int count, cudaStream_t s);
+
+// specialised (compile-time library, register-resident, TMA-staged) fused train step.
+// `w` is Ξ; `mask` (may be NULL) is multiplied in while packing W into the constant bank; `co` (may be NULL)
+// requests the closure epilogue inside the kernel's last block.
 bool fused_supported(const LibTab& t, uint32_t flags);
 const char* fused_variant_name(const LibTab& t, uint32_t flags);
-int fused_train_step(const float* x, const float* dx, int64_t n, const LibTab& t, const float* w,
-                     uint32_t flags, double* out, void* ws, int64_t ws_bytes, cudaStream_t s);
+int fused_train_step(const float* x, const float* dx, int64_t n, const LibTab& t, const float* w, const float* mask,
+                     uint32_t flags, double* out, const ClosureOut* co, void* ws, int64_t ws_bytes, cudaStream_t s);
 int64_t fused_workspace_bytes(const LibTab& t);
 
 // rollout

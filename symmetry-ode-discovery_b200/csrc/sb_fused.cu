@@ -2,7 +2,7 @@
 //
 // Replaces, in ONE pass over (x, dx), the reference's `regressor(x)` (Θ materialised column by column,
 // `sindy.py:79-82`), `MSELoss` (`train.py:663-664`) and the Θ-side of `loss.backward()` (`train.py:689`):
-//   r = Θ(x)·Wᵀ − dx,   out = { Σ r², Σ_n r_i Θ_k }.
+//   r = Θ(x)·Wᵀ − dx,   out = { Σ r², Σ_n r_i Θ_k }   [+ loss and dL/dΞ when the closure epilogue is requested].
 // Θ never exists in memory: each thread expands the K monomials of its sample in registers by the
 // parent*variable recurrence, forms the d predictions, and accumulates the d×K outer product r ⊗ Θ into
 // private fp32 accumulators. All d·K FMAs of the prediction and of the gradient are issued as packed
@@ -11,10 +11,13 @@
 // accumulators.
 //
 // Data movement: x and dx tiles are streamed HBM -> shared memory with 1-D TMA bulk copies
-// (cp.async.bulk ... mbarrier::complete_tx, SASS UBLKCP) into a kStages-deep ring, one elected thread issuing,
-// every thread waiting on the stage's mbarrier; X and dX are read exactly once, 8·d bytes per sample.
-// Grid = resident CTAs (multiple of the SM count), static round-robin tile assignment, per-CTA partials in
-// fp64 and an ordered last-block reduction => deterministic results.
+// (cp.async.bulk ... mbarrier::complete_tx, SASS UBLKCP) into a kStages-deep ring. A "full" mbarrier per stage
+// carries the transaction bytes; an "empty" mbarrier per stage counts one arrival per warp, so the elected
+// producer thread refills a stage without any CTA-wide barrier in the steady state. X and dX are read exactly
+// once, 8·d bytes per sample. Grid = resident CTAs (multiple of the SM count), static round-robin tile
+// assignment, per-CTA partials in fp64 and an ordered last-block reduction => deterministic results.
+#include <cstdlib>
+
 #include "sb_common.cuh"
 
 namespace sb {
@@ -35,6 +38,9 @@ __device__ __forceinline__ void fence_mbar_init() {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
   asm volatile(
@@ -58,27 +64,33 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // ---- configuration per library ------------------------------------------------------------------
-template <int D, int P>
+// VAR selects a tuning variant (A/B-tested on the B200):
+//   bit 0: 1 = per-stage "empty" mbarriers (no __syncthreads in the tile loop), 0 = CTA barrier per tile
+//   bit 1: 1 = two partial sums per equation in the prediction, 0 = one
+template <int D, int P, int VAR = 1>
 struct Cfg {
   static constexpr int K = Poly<D, P>::K;
   static constexpr int K2 = (K + 1) / 2;     // packed column pairs
   static constexpr int NV = D * K + 1;       // values reduced per CTA (grad + loss)
   static constexpr int kThreads = 256;
+  static constexpr int kWarps = kThreads / 32;
   static constexpr int kTile = 1024;         // samples per stage
   static constexpr int kStages = 4;
+  static constexpr bool kEmptyBarriers = (VAR & 1) != 0;
+  static constexpr int kChains = (VAR & 2) ? 2 : 1;
   // accumulators dominate the register budget: D*K2*2 of them
   static constexpr int kMinBlocks = (D * K2 * 2 + K > 150) ? 1 : ((D * K2 * 2 + K > 40) ? 2 : 3);
   static constexpr size_t kSmemData = (size_t)kStages * 2 * kTile * D * sizeof(float);
-  static constexpr size_t kSmemBytes = kSmemData + kStages * sizeof(uint64_t) + 16;
+  static constexpr size_t kSmemBytes = kSmemData + 2 * kStages * sizeof(uint64_t) + 16;
 };
 
 enum { LEFT_RESIDUAL = 0, LEFT_DX = 1 };
 
 // one sample: expand Θ, predict, accumulate r ⊗ Θ
-template <int D, int P, int LEFT>
+template <int D, int P, int LEFT, int VAR>
 __device__ __forceinline__ void accumulate_sample(const float (&xs)[D], const float (&ds)[D],
-                                                  float2 (&acc)[D][Cfg<D, P>::K2], float& lacc) {
-  using C = Cfg<D, P>;
+                                                  float2 (&acc)[D][Cfg<D, P, VAR>::K2], float& lacc) {
+  using C = Cfg<D, P, VAR>;
   float m[C::K];
   expand_poly<D, P>(xs, m);
   float2 m2[C::K2];
@@ -88,17 +100,20 @@ __device__ __forceinline__ void accumulate_sample(const float (&xs)[D], const fl
   });
   float r[D];
   if constexpr (LEFT == LEFT_RESIDUAL) {
-    float2 pred[D];
-    static_for<0, D>([&](auto i) { pred[i] = make_float2(0.f, 0.f); });
+    constexpr int NC = C::kChains;
+    float2 pred[D][NC];
+    static_for<0, D>([&](auto i) { static_for<0, NC>([&](auto c) { pred[i][c] = make_float2(0.f, 0.f); }); });
     static_for<0, C::K2>([&](auto kc) {
       constexpr int kk = kc;
       static_for<0, D>([&](auto ic) {
         constexpr int i = ic;
-        pred[i] = __ffma2_rn(c_w2[i * C::K2 + kk], m2[kk], pred[i]);
+        pred[i][kk % NC] = __ffma2_rn(c_w2[i * C::K2 + kk], m2[kk], pred[i][kk % NC]);
       });
     });
     static_for<0, D>([&](auto i) {
-      r[i] = (pred[i].x + pred[i].y) - ds[i];
+      float s = pred[i][0].x + pred[i][0].y;
+      static_for<1, NC>([&](auto c) { s += pred[i][c].x + pred[i][c].y; });
+      r[i] = s - ds[i];
       lacc = fmaf(r[i], r[i], lacc);
     });
   } else {
@@ -122,23 +137,32 @@ struct FusedArgs {
   int64_t n_tiles;
   double* partial;    // [grid][NV]
   unsigned int* ticket;
-  double* out;        // packed output base
+  double* out;        // packed output base (may be NULL when only the closure epilogue is wanted)
   int64_t out_off;    // offset of this section's d×K block
   int out_transposed; // 0: [i*K+k], 1: [k*d+i]  (b section)
   int write_header;   // write out[0] (loss) and out[1] (n)
+  // optional closure epilogue (single-rank): loss = Σr²/(n d) + w_l1‖Ξ‖₁, grad = 2/(n d)·Σ r⊗Θ ⊙ mask + w_l1 sign(Ξ)
+  const float* xi;
+  const float* mask;
+  double w_l1;
+  float* loss_out;
+  float* grad_out;
 };
 
-template <int D, int P, int LEFT>
-__global__ void __launch_bounds__(Cfg<D, P>::kThreads, Cfg<D, P>::kMinBlocks)
+template <int D, int P, int LEFT, int VAR>
+__global__ void __launch_bounds__(Cfg<D, P, VAR>::kThreads, Cfg<D, P, VAR>::kMinBlocks)
 fused_step_kernel(FusedArgs a) {
-  using C = Cfg<D, P>;
+  using C = Cfg<D, P, VAR>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* tiles = reinterpret_cast<float*>(smem_raw);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + C::kSmemData);
-  __shared__ float red[C::kThreads / 32][C::NV];
+  uint64_t* empty = full + C::kStages;
+  __shared__ float red[C::kWarps][C::NV];
+  __shared__ double fin[C::NV + 1];
   __shared__ int is_last;
 
   const int tid = threadIdx.x;
+  const int lane = tid & 31, wid = tid >> 5;
   constexpr int kTileFloats = C::kTile * D;
 
   auto tile_count = [&](int64_t tile) -> int {
@@ -155,7 +179,7 @@ fused_step_kernel(FusedArgs a) {
   };
 
   if (tid == 0) {
-    for (int s = 0; s < C::kStages; ++s) mbar_init(&full[s], 1);
+    for (int s = 0; s < C::kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], C::kWarps); }
     fence_mbar_init();
   }
   __syncthreads();
@@ -176,6 +200,17 @@ fused_step_kernel(FusedArgs a) {
   for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
     const int stage = it % C::kStages;
     const uint32_t parity = (uint32_t)(it / C::kStages) & 1u;
+    if constexpr (C::kEmptyBarriers) {
+      // refill the stage consumed one iteration ago: by now every warp has (almost surely) released it
+      if (tid == 0 && it > 0) {
+        const int64_t next = tile + (int64_t)(C::kStages - 1) * gridDim.x;
+        if (next < a.n_tiles) {
+          const int ps = (it - 1) % C::kStages;
+          mbar_wait(&empty[ps], (uint32_t)((it - 1) / C::kStages) & 1u);
+          issue(next, ps);
+        }
+      }
+    }
     mbar_wait(&full[stage], parity);
     const float* sx = tiles + (size_t)stage * 2 * kTileFloats;
     const float* sd = sx + kTileFloats;
@@ -184,12 +219,17 @@ fused_step_kernel(FusedArgs a) {
     for (int j = tid; j < cnt; j += C::kThreads) {
       float xs[D], ds[D];
       static_for<0, D>([&](auto q) { xs[q] = sx[j * D + q]; ds[q] = sd[j * D + q]; });
-      accumulate_sample<D, P, LEFT>(xs, ds, acc, lacc);
+      accumulate_sample<D, P, LEFT, VAR>(xs, ds, acc, lacc);
     }
-    __syncthreads();  // every thread is done with this stage before it is refilled
-    if (tid == 0) {
-      const int64_t next = tile + (int64_t)C::kStages * gridDim.x;
-      if (next < a.n_tiles) issue(next, stage);
+    if constexpr (C::kEmptyBarriers) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[stage]);   // this warp is done with the stage
+    } else {
+      __syncthreads();  // every thread is done with this stage before it is refilled
+      if (tid == 0) {
+        const int64_t next = tile + (int64_t)C::kStages * gridDim.x;
+        if (next < a.n_tiles) issue(next, stage);
+      }
     }
   }
 
@@ -199,12 +239,11 @@ fused_step_kernel(FusedArgs a) {
     if (j < a.n) {
       float xs[D], ds[D];
       static_for<0, D>([&](auto q) { xs[q] = __ldg(a.x + j * D + q); ds[q] = __ldg(a.dx + j * D + q); });
-      accumulate_sample<D, P, LEFT>(xs, ds, acc, lacc);
+      accumulate_sample<D, P, LEFT, VAR>(xs, ds, acc, lacc);
     }
   }
 
   // ---- CTA reduction: shuffles within the warp, fp64 across warps ----
-  const int lane = tid & 31, wid = tid >> 5;
   static_for<0, D>([&](auto ic) {
     constexpr int i = ic;
     static_for<0, C::K2>([&](auto kc) {
@@ -226,7 +265,7 @@ fused_step_kernel(FusedArgs a) {
   for (int e = tid; e < C::NV; e += C::kThreads) {
     double v = 0.0;
 #pragma unroll
-    for (int wq = 0; wq < C::kThreads / 32; ++wq) v += (double)red[wq][e];
+    for (int wq = 0; wq < C::kWarps; ++wq) v += (double)red[wq][e];
     mine[e] = v;
   }
   __threadfence();
@@ -240,21 +279,73 @@ fused_step_kernel(FusedArgs a) {
   for (int e = tid; e < C::NV; e += C::kThreads) {
     double v = 0.0;
     for (unsigned int b = 0; b < gridDim.x; ++b) v += a.partial[(int64_t)b * C::NV + e];
-    if (e == C::NV - 1) {
-      if (a.write_header) { a.out[0] = v; a.out[1] = (double)a.n; }
-    } else {
-      const int i = e / C::K, k = e % C::K;
-      a.out[a.out_off + (a.out_transposed ? (int64_t)k * D + i : (int64_t)e)] = v;
+    fin[e] = v;
+    if (a.out) {
+      if (e == C::NV - 1) {
+        if (a.write_header) { a.out[0] = v; a.out[1] = (double)a.n; }
+      } else {
+        const int i = e / C::K, k = e % C::K;
+        a.out[a.out_off + (a.out_transposed ? (int64_t)k * D + i : (int64_t)e)] = v;
+      }
     }
   }
   if (tid == 0) *a.ticket = 0u;
+
+  // ---- closure epilogue (`train.py:663-664,680-683,689`) ----
+  if (a.grad_out || a.loss_out) {
+    __syncthreads();
+    const double denom = (double)(a.n > 0 ? a.n : 1) * D;
+    double l1 = 0.0;
+    for (int e = tid; e < D * C::K; e += C::kThreads) {
+      const float xi = a.xi[e];
+      const float mk = a.mask ? a.mask[e] : 1.f;
+      l1 += fabs((double)xi);
+      if (a.grad_out) {
+        const double sgn = (xi > 0.f) ? 1.0 : ((xi < 0.f) ? -1.0 : 0.0);
+        a.grad_out[e] = (float)(fin[e] * (2.0 / denom) * (double)mk + a.w_l1 * sgn);
+      }
+    }
+    l1 = warp_sum(l1);
+    __shared__ double l1w[C::kWarps];
+    if (lane == 0) l1w[wid] = l1;
+    __syncthreads();
+    if (tid == 0 && a.loss_out) {
+      double t = 0.0;
+      for (int wq = 0; wq < C::kWarps; ++wq) t += l1w[wq];
+      *a.loss_out = (float)(fin[C::NV - 1] / denom + a.w_l1 * t);
+    }
+  }
+}
+
+// Ξ (d×K fp32) [⊙ mask] -> the packed constant slot of the fused kernels (pairs, zero padded for odd K)
+__global__ void pack_w_kernel(const float* __restrict__ xi, const float* __restrict__ mask, float* __restrict__ dst,
+                              int d, int K, int K2) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= d * K2 * 2) return;
+  const int i = t / (2 * K2), k = t % (2 * K2);
+  float v = 0.f;
+  if (k < K) {
+    v = xi[i * K + k];
+    if (mask) v *= mask[i * K + k];
+  }
+  dst[t] = v;
 }
 
 // ---- host side ------------------------------------------------------------------------------------
-template <int D, int P, int LEFT>
-int launch_fused(FusedArgs a, void* ws, int64_t ws_bytes, cudaStream_t s) {
-  using C = Cfg<D, P>;
-  auto kern = fused_step_kernel<D, P, LEFT>;
+int tuning_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SB_FUSED_VARIANT");
+    v = e ? atoi(e) : 1;
+    if (v < 0 || v > 3) v = 1;
+  }
+  return v;
+}
+
+template <int D, int P, int LEFT, int VAR>
+int launch_fused_var(FusedArgs a, void* ws, int64_t ws_bytes, cudaStream_t s) {
+  using C = Cfg<D, P, VAR>;
+  auto kern = fused_step_kernel<D, P, LEFT, VAR>;
   static int grid_cached[64] = {0};  // per device
   int dev = 0;
   SB_CUDA_TRY(cudaGetDevice(&dev));
@@ -285,36 +376,53 @@ int launch_fused(FusedArgs a, void* ws, int64_t ws_bytes, cudaStream_t s) {
   return SB_OK;
 }
 
-// W (d×K fp32, device) -> packed constant slot, stream-ordered
-template <int D, int P>
-int upload_w(const float* w, cudaStream_t s) {
-  using C = Cfg<D, P>;
-  if (C::K % 2 == 0) {
-    SB_CUDA_TRY(cudaMemcpyToSymbolAsync(c_w2, w, sizeof(float) * D * C::K, 0, cudaMemcpyDeviceToDevice, s));
-  } else {
-    void* base = nullptr;
-    SB_CUDA_TRY(cudaGetSymbolAddress(&base, c_w2));
-    SB_CUDA_TRY(cudaMemsetAsync(base, 0, sizeof(float2) * D * C::K2, s));
-    for (int i = 0; i < D; ++i)
-      SB_CUDA_TRY(cudaMemcpyToSymbolAsync(c_w2, w + i * C::K, sizeof(float) * C::K,
-                                          sizeof(float2) * (size_t)i * C::K2, cudaMemcpyDeviceToDevice, s));
+template <int D, int P, int LEFT>
+int launch_fused(const FusedArgs& a, void* ws, int64_t ws_bytes, cudaStream_t s) {
+  if constexpr (D == 3 && P == 5) {  // the headline shape carries the A/B variants
+    switch (tuning_variant()) {
+      case 0: return launch_fused_var<D, P, LEFT, 0>(a, ws, ws_bytes, s);
+      case 2: return launch_fused_var<D, P, LEFT, 2>(a, ws, ws_bytes, s);
+      case 3: return launch_fused_var<D, P, LEFT, 3>(a, ws, ws_bytes, s);
+      default: break;
+    }
   }
+  return launch_fused_var<D, P, LEFT, 1>(a, ws, ws_bytes, s);
+}
+
+// Ξ [⊙ mask] -> constant slot, one tiny launch on the stream (replaces a D2D cudaMemcpyToSymbolAsync + a mul)
+template <int D, int P>
+int upload_w(const float* xi, const float* mask, cudaStream_t s) {
+  using C = Cfg<D, P>;
+  static float* base[64] = {nullptr};
+  int dev = 0;
+  SB_CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) { set_error("device index %d out of range", dev); return SB_ERR_INVALID; }
+  if (!base[dev]) {
+    void* p = nullptr;
+    SB_CUDA_TRY(cudaGetSymbolAddress(&p, c_w2));
+    base[dev] = reinterpret_cast<float*>(p);
+  }
+  const int total = D * C::K2 * 2;
+  pack_w_kernel<<<(total + 255) / 256, 256, 0, s>>>(xi, mask, base[dev], D, C::K, C::K2);
+  SB_LAUNCH_CHECK("pack_w_kernel");
   return SB_OK;
 }
 
 template <int D, int P>
-int run_fused(const float* x, const float* dx, int64_t n, const float* w, uint32_t flags, double* out, void* ws,
-              int64_t ws_bytes, cudaStream_t s) {
+int run_fused(const float* x, const float* dx, int64_t n, const float* w, const float* mask, uint32_t flags,
+              double* out, const ClosureOut* co, void* ws, int64_t ws_bytes, cudaStream_t s) {
   using C = Cfg<D, P>;
   FusedArgs a{};
   a.x = x; a.dx = dx; a.n = n; a.out = out;
   const bool resid = flags & (SB_STEP_LOSS | SB_STEP_GRAD);
   if (resid) {
-    int st = upload_w<D, P>(w, s);
+    int st = upload_w<D, P>(w, mask, s);
     if (st != SB_OK) return st;
     a.out_off = 2; a.out_transposed = 0; a.write_header = 1;
+    if (co) { a.xi = w; a.mask = mask; a.w_l1 = co->w_l1; a.loss_out = co->loss; a.grad_out = co->grad; }
     st = launch_fused<D, P, LEFT_RESIDUAL>(a, ws, ws_bytes, s);
     if (st != SB_OK) return st;
+    a.loss_out = nullptr; a.grad_out = nullptr;
   }
   if (flags & SB_STEP_B) {
     a.out_off = 2 + ((flags & SB_STEP_GRAD) ? (int64_t)D * C::K : 0);
@@ -333,7 +441,7 @@ int run_fused(const float* x, const float* dx, int64_t n, const float* w, uint32
 bool fused_supported(const LibTab& t, uint32_t flags) {
   if (t.sine || t.exp_) return false;
   if (flags & SB_STEP_GRAM) return false;
-  // LOSS without GRAD still runs the residual kernel (the gradient section is simply not reported)
+  // LOSS without GRAD runs the generic residual rows (the fused kernel always accumulates the gradient)
   if ((flags & SB_STEP_LOSS) && !(flags & SB_STEP_GRAD)) return false;
 #define X(D, P) if (t.d == D && t.n_poly == n_poly_terms(D, P)) return true;
   SB_FUSED_SHAPES(X)
@@ -353,10 +461,11 @@ int64_t fused_workspace_bytes(const LibTab& t) {
   return kWsHeaderBytes + (int64_t)kMaxPartialBlocks * ((int64_t)t.d * t.K + 1) * (int64_t)sizeof(double);
 }
 
-int fused_train_step(const float* x, const float* dx, int64_t n, const LibTab& t, const float* w, uint32_t flags,
-                     double* out, void* ws, int64_t ws_bytes, cudaStream_t s) {
-#define X(D, P) \
-  if (t.d == D && t.n_poly == n_poly_terms(D, P)) return run_fused<D, P>(x, dx, n, w, flags, out, ws, ws_bytes, s);
+int fused_train_step(const float* x, const float* dx, int64_t n, const LibTab& t, const float* w, const float* mask,
+                     uint32_t flags, double* out, const ClosureOut* co, void* ws, int64_t ws_bytes, cudaStream_t s) {
+#define X(D, P)                                                  \
+  if (t.d == D && t.n_poly == n_poly_terms(D, P))                \
+    return run_fused<D, P>(x, dx, n, w, mask, flags, out, co, ws, ws_bytes, s);
   SB_FUSED_SHAPES(X)
 #undef X
   set_error("no fused kernel for d=%d K=%d", t.d, t.K);

@@ -361,12 +361,61 @@ int launch_rows(const LibTab& t, RowsArgs a, void* ws, int64_t ws_bytes, cudaStr
   return SB_OK;
 }
 
+// loss = Σr²/(n·d) + w_l1·‖Ξ‖₁ ; grad = 2/(n·d)·(Σ r⊗Θ)⊙mask + w_l1·sign(Ξ)   (`train.py:663-664,680-683,689`)
+__global__ void __launch_bounds__(kThreads) epilogue_kernel(const double* __restrict__ packed, int d, int K,
+                                                            const float* __restrict__ xi,
+                                                            const float* __restrict__ mask, double w_l1,
+                                                            float* __restrict__ loss_out,
+                                                            float* __restrict__ grad_out) {
+  __shared__ double l1w[kThreads / 32];
+  const double n = packed[1];
+  const double denom = (n > 0.0 ? n : 1.0) * d;
+  double l1 = 0.0;
+  for (int e = threadIdx.x; e < d * K; e += blockDim.x) {
+    const float v = xi[e];
+    const float mk = mask ? mask[e] : 1.f;
+    l1 += fabs((double)v);
+    if (grad_out) {
+      const double sgn = (v > 0.f) ? 1.0 : ((v < 0.f) ? -1.0 : 0.0);
+      grad_out[e] = (float)(packed[2 + e] * (2.0 / denom) * (double)mk + w_l1 * sgn);
+    }
+  }
+  l1 = warp_sum(l1);
+  if ((threadIdx.x & 31) == 0) l1w[threadIdx.x >> 5] = l1;
+  __syncthreads();
+  if (threadIdx.x == 0 && loss_out) {
+    double t = 0.0;
+    for (int wq = 0; wq < kThreads / 32; ++wq) t += l1w[wq];
+    *loss_out = (float)(packed[0] / denom + w_l1 * t);
+  }
+}
+
+__global__ void mask_mul_kernel(const float* __restrict__ xi, const float* __restrict__ mask, float* __restrict__ dst,
+                                int count) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < count) dst[t] = mask ? xi[t] * mask[t] : xi[t];
+}
+
 }  // namespace
 
+int step_epilogue(const double* packed, const LibTab& t, const float* xi, const float* mask, double w_l1,
+                  float* loss_out, float* grad_out, cudaStream_t s) {
+  epilogue_kernel<<<1, kThreads, 0, s>>>(packed, t.d, t.K, xi, mask, w_l1, loss_out, grad_out);
+  SB_LAUNCH_CHECK("epilogue_kernel");
+  return SB_OK;
+}
+
+int mask_mul(const float* xi, const float* mask, float* dst, int count, cudaStream_t s) {
+  mask_mul_kernel<<<(count + 255) / 256, 256, 0, s>>>(xi, mask, dst, count);
+  SB_LAUNCH_CHECK("mask_mul_kernel");
+  return SB_OK;
+}
+
 int64_t generic_workspace_bytes(const LibTab& t) {
-  // worst case over row counts r in [1, 2d+K]: r * ceil(cap/r) <= cap + r
+  // worst case over row counts r in [1, 2d+K]: r * ceil(cap/r) <= cap + r; plus a d×K fp32 scratch for Ξ⊙mask
   const int64_t r = max_rows(t);
-  return kWsHeaderBytes + (int64_t)(kMaxPartialBlocks + r) * (t.K + 1) * (int64_t)sizeof(double);
+  return kWsHeaderBytes + (int64_t)(kMaxPartialBlocks + r) * (t.K + 1) * (int64_t)sizeof(double) +
+         (int64_t)t.d * t.K * (int64_t)sizeof(float) + 256;
 }
 
 int generic_theta(const float* x, int64_t n, const LibTab& t, float* theta, cudaStream_t s) {

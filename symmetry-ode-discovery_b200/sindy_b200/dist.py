@@ -5,7 +5,10 @@ fused kernel over its own samples and obtains the packed fp64 SUMS `[Î£rÂ², n, Î
 (see include/sindy_b200.h). Sums â€” not per-rank means â€” are all-reduced, then every rank divides by the GLOBAL
 nÂ·d, so the loss/gradient equal the single-process values for any (uneven) sharding and Îž / mask / optimiser
 state stay replicated without further communication. The message is dÂ·K+2 doubles (1.4 KB for d=3, K=56):
-latency-bound, so the whole step (W upload, kernel, all-reduce, epilogue) is captured in a CUDA graph.
+latency-bound, so the whole step (W packing, kernel, all-reduce, epilogue) can be captured in a CUDA graph.
+
+Launch counts per closure: single rank = 2 (pack ÎžâŠ™mask into the constant bank; fused kernel whose last block
+writes loss and gradient). Multi rank = 3 + the all-reduce (mask multiply + pack, fused kernel, epilogue).
 
 `HostStreamedStep` is the host-buffer entry point: x/dx live in pinned host memory and are streamed through
 two device staging buffers on two copy streams while the kernel consumes the previous chunk.
@@ -27,9 +30,8 @@ def _world(group) -> int:
 
 def mse_from_sums(packed: torch.Tensor, lib: Library, w: torch.Tensor, mask: Optional[torch.Tensor] = None,
                   w_l1: float = 0.0, params_l1: Optional[torch.Tensor] = None):
-    """Epilogue on the (all-reduced) packed sums: loss = Î£rÂ²/(nÂ·d) [+ w_l1Â·â€–Îžâ€–â‚] and dL/dÎž
-    (`train.py:663-664,680-683,689`). `w` is only used for its dtype/shape; `params_l1` (default: none) is the
-    unmasked parameter tensor of the L1 term."""
+    """Epilogue on the (all-reduced) packed sums in plain torch ops: loss = Î£rÂ²/(nÂ·d) [+ w_l1Â·â€–Îžâ€–â‚] and dL/dÎž
+    (`train.py:663-664,680-683,689`). Device-agnostic twin of sb_step_epilogue (used by the gloo tests)."""
     d, K = lib.dim, lib.K
     denom = packed[1] * d
     loss = packed[0] / denom
@@ -43,65 +45,98 @@ def mse_from_sums(packed: torch.Tensor, lib: Library, w: torch.Tensor, mask: Opt
 
 
 class ShardedTrainStep:
-    """loss, grad = step(W) over samples sharded across the ranks of `group` (or a single process).
+    """loss, grad = step(Îž, mask) over samples sharded across the ranks of `group` (or a single process).
 
     local_sums: callable (W) -> packed fp64 sums of THIS rank's shard. The default runs the CUDA kernel on
     (x, dx); tests inject a CPU stand-in to exercise the combine logic with the gloo backend.
+    sgd_lr: if set, `Îž -= sgd_lrÂ·grad` is applied to the (static) parameters inside the step â€” a stand-in for the
+    optimiser update so that consecutive benchmark steps see different coefficients.
     """
 
     def __init__(self, lib: Library, x: Optional[torch.Tensor] = None, dx: Optional[torch.Tensor] = None,
                  flags: int = native.SB_STEP_LOSS | native.SB_STEP_GRAD, group=None,
-                 local_sums: Optional[Callable[[torch.Tensor], torch.Tensor]] = None, use_graph: bool = False):
+                 local_sums: Optional[Callable[[torch.Tensor], torch.Tensor]] = None, use_graph: bool = False,
+                 sgd_lr: Optional[float] = None):
         self.lib, self.flags, self.group = lib, flags, group
         self.x, self.dx = x, dx
         self._custom = local_sums
-        self._out = None
-        self._graph = None
         self._use_graph = use_graph and local_sums is None
-        self._static_w = None
-        self._static_res = None
+        self._sgd_lr = sgd_lr
+        self._graph = None
+        self._bufs = None
+        self.xi = None      # static parameters (graph mode / sgd mode)
+        self.mask = None
 
     # -- pieces ----------------------------------------------------------------------------------------
+    def _buffers(self, dev):
+        if self._bufs is None:
+            d, K = self.lib.dim, self.lib.K
+            self._bufs = (torch.empty(self.lib.step_out_len(self.flags), dtype=torch.float64, device=dev),
+                          torch.empty((), dtype=torch.float32, device=dev),
+                          torch.empty(d, K, dtype=torch.float32, device=dev))
+        return self._bufs
+
     def local_sums(self, w: torch.Tensor) -> torch.Tensor:
         if self._custom is not None:
             return self._custom(w)
-        if self._out is None:
-            self._out = torch.empty(self.lib.step_out_len(self.flags), dtype=torch.float64, device=self.x.device)
-        return native.train_step(self.x, self.dx, w, self.lib, self.flags, out=self._out)
+        packed, _, _ = self._buffers(self.x.device)
+        return native.train_step(self.x, self.dx, w, self.lib, self.flags, out=packed)
 
-    def reduced_sums(self, w: torch.Tensor) -> torch.Tensor:
-        packed = self.local_sums(w)
-        if _world(self.group) > 1:
+    def closure(self, xi: torch.Tensor, mask: Optional[torch.Tensor], w_l1: float):
+        """(loss, dL/dÎž): the eager step."""
+        world = _world(self.group)
+        if self._custom is not None:
+            wm = xi if mask is None else xi * mask
+            packed = self._custom(wm)
+            if world > 1:
+                dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=self.group)
+            return mse_from_sums(packed, self.lib, xi, mask, w_l1, xi if w_l1 != 0.0 else None)
+        packed, loss, grad = self._buffers(self.x.device)
+        if world == 1:
+            native.closure(self.x, self.dx, xi, mask, self.lib, w_l1, packed=packed, loss=loss, grad=grad)
+        else:
+            wm = xi if mask is None else xi * mask
+            native.train_step(self.x, self.dx, wm, self.lib, self.flags, out=packed)
             dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=self.group)
-        return packed
+            native.step_epilogue(packed, xi, mask, self.lib, w_l1, loss=loss, grad=grad)
+        return loss, grad
 
-    def _eager(self, w, mask, w_l1, params_l1):
-        wm = w if mask is None else w * mask
-        packed = self.reduced_sums(wm)
-        return mse_from_sums(packed, self.lib, w, mask, w_l1, params_l1)
+    def _body(self, w_l1):
+        loss, grad = self.closure(self.xi, self.mask, w_l1)
+        if self._sgd_lr is not None:
+            self.xi.add_(grad, alpha=-self._sgd_lr)
+        return loss, grad
 
     # -- public ----------------------------------------------------------------------------------------
-    def step(self, w: torch.Tensor, mask: Optional[torch.Tensor] = None, w_l1: float = 0.0):
-        """One closure evaluation: (loss, dL/dÎž) with Îž = w (unmasked parameters) and optional mask."""
+    def step(self, xi: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None, w_l1: float = 0.0):
+        """One closure evaluation. With use_graph or sgd_lr the parameters are static: pass `xi` to (re)load them,
+        or None to keep the current ones (sgd mode advances them in place)."""
+        if not self._use_graph and self._sgd_lr is None:
+            return self.closure(xi, mask, w_l1)
+        if self.xi is None:
+            if xi is None:
+                raise ValueError("the first call needs the parameters")
+            self.xi = xi.detach().clone()
+            self.mask = None if mask is None else mask.detach().clone()
+        elif xi is not None:
+            self.xi.copy_(xi)
+            if mask is not None:
+                self.mask.copy_(mask)
         if not self._use_graph:
-            return self._eager(w, mask, w_l1, w if w_l1 != 0.0 else None)
+            return self._body(w_l1)
         if self._graph is None:
-            self._static_w = w.detach().clone()
-            self._static_mask = None if mask is None else mask.detach().clone()
-            # warm-up on a side stream (allocations, NCCL channel setup) before capture
-            s = torch.cuda.Stream()
-            s.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(s):
+            keep = self.xi.clone()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):  # warm-up outside capture: allocations, NCCL channels, occupancy queries
                 for _ in range(3):
-                    self._eager(self._static_w, self._static_mask, w_l1, self._static_w if w_l1 else None)
-            torch.cuda.current_stream().wait_stream(s)
+                    self._body(w_l1)
+            torch.cuda.current_stream().wait_stream(side)
+            self.xi.copy_(keep)
             self._graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self._graph):
-                self._static_res = self._eager(self._static_w, self._static_mask, w_l1,
-                                               self._static_w if w_l1 else None)
-        self._static_w.copy_(w)
-        if mask is not None:
-            self._static_mask.copy_(mask)
+                self._static_res = self._body(w_l1)
+            self.xi.copy_(keep)
         self._graph.replay()
         return self._static_res
 

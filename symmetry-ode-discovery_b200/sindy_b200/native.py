@@ -48,6 +48,10 @@ _SIGNATURES = {
                                 c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "sb_train_step": (c_int, [c_void_p, c_void_p, c_int64, POINTER(_CLibrary), c_void_p, c_uint32, c_void_p,
                               c_void_p, c_int64, c_void_p]),
+    "sb_closure": (c_int, [c_void_p, c_void_p, c_int64, POINTER(_CLibrary), c_void_p, c_void_p, c_double, c_void_p,
+                           c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "sb_step_epilogue": (c_int, [c_void_p, POINTER(_CLibrary), c_void_p, c_void_p, c_double, c_void_p, c_void_p,
+                                 c_void_p]),
     "sb_train_step_variant": (c_char_p, [POINTER(_CLibrary), c_uint32]),
     "sb_rollout": (c_int, [c_void_p, c_int64, POINTER(_CLibrary), c_void_p, c_double, c_int64, c_int64, c_int,
                            c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -267,6 +271,50 @@ def train_step(x: torch.Tensor, dx: Optional[torch.Tensor], w: Optional[torch.Te
         _check(load().sb_train_step(xf.data_ptr(), _ptr(dxf), xf.shape[0], ctypes.byref(lib.c()), _ptr(wf), flags,
                                     out.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev)), "sb_train_step")
     return out
+
+
+def closure(x: torch.Tensor, dx: torch.Tensor, xi: torch.Tensor, mask: Optional[torch.Tensor], lib: Library,
+            w_l1: float = 0.0, packed: Optional[torch.Tensor] = None, loss: Optional[torch.Tensor] = None,
+            grad: Optional[torch.Tensor] = None):
+    """One closure evaluation (`train.py:645-690` without sym-reg): returns (loss fp32 scalar tensor, dL/dΞ fp32
+    (d×K), packed fp64 sums). xi is the unmasked parameter matrix. Output tensors may be passed in for reuse
+    (CUDA-graph friendly)."""
+    xf = _flat(_f32c(x, "x"), lib.dim, "x")
+    dxf = _flat(_f32c(dx, "dx"), lib.dim, "dx")
+    xi = _f32c(xi, "xi")
+    mk = _f32c(mask, "mask") if mask is not None else None
+    dev = xf.device
+    d, K = lib.dim, lib.K
+    if packed is None:
+        packed = torch.empty(2 + d * K, dtype=torch.float64, device=dev)
+    if loss is None:
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+    if grad is None:
+        grad = torch.empty(d, K, dtype=torch.float32, device=dev)
+    ws = _workspace(lib, dev)
+    with torch.cuda.device(dev):
+        _check(load().sb_closure(xf.data_ptr(), dxf.data_ptr(), xf.shape[0], ctypes.byref(lib.c()), xi.data_ptr(),
+                                 _ptr(mk), float(w_l1), packed.data_ptr(), loss.data_ptr(), grad.data_ptr(),
+                                 ws.data_ptr(), ws.numel(), _stream(dev)), "sb_closure")
+    return loss, grad, packed
+
+
+def step_epilogue(packed: torch.Tensor, xi: torch.Tensor, mask: Optional[torch.Tensor], lib: Library,
+                  w_l1: float = 0.0, loss: Optional[torch.Tensor] = None, grad: Optional[torch.Tensor] = None):
+    """loss and dL/dΞ from packed sums that were all-reduced over the ranks (one launch)."""
+    if not packed.is_cuda or packed.dtype != torch.float64:
+        raise RuntimeError("sindy_b200: `packed` must be a CUDA float64 tensor")
+    xi = _f32c(xi, "xi")
+    mk = _f32c(mask, "mask") if mask is not None else None
+    dev = packed.device
+    if loss is None:
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+    if grad is None:
+        grad = torch.empty(lib.dim, lib.K, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _check(load().sb_step_epilogue(packed.data_ptr(), ctypes.byref(lib.c()), xi.data_ptr(), _ptr(mk), float(w_l1),
+                                       loss.data_ptr(), grad.data_ptr(), _stream(dev)), "sb_step_epilogue")
+    return loss, grad
 
 
 def train_step_variant(lib: Library, flags: int = SB_STEP_LOSS | SB_STEP_GRAD) -> str:

@@ -415,3 +415,78 @@ def test_golden_lbfgs_fit(nat, golden):
         Xi = reg.get_Xi() if reg.constraint else reg.Xi
         assert np.array_equal(reg.mask.cpu().numpy(), g[tag + "_mask"]), tag
         assert rel(Xi * reg.mask, g[tag + "_Xi"] * g[tag + "_mask"]) < 1e-3, tag
+
+
+# ---------------------------------------------------------------------------------------------------------
+# closure entry points (2-launch closure, multi-GPU epilogue) and the sharded step wrapper
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("d,p,s,e", [(3, 5, 0, 0), (2, 2, 0, 0), (2, 3, 0, 0), (3, 3, 1, 1), (2, 2, 0, 1), (4, 3, 0, 0)])
+@pytest.mark.parametrize("n", [5, 4099, 300_001])
+def test_closure_and_epilogue_vs_oracle(nat, d, p, s, e, n):
+    rng = np.random.default_rng(n + d)
+    lib = nat.Library(d, p, bool(s), bool(e))
+    K = lib.K
+    x = rng.uniform(-1, 1, (n, d)).astype(np.float32)
+    dx = rng.standard_normal((n, d)).astype(np.float32)
+    Xi = rng.standard_normal((d, K)).astype(np.float32)
+    Xi[0, 0] = 0.0                                            # sign(0) = 0 in the L1 subgradient
+    mask = (rng.random((d, K)) > 0.3).astype(np.float32)
+    w_l1 = 0.01
+    ref_loss, ref_grad = O.mse_loss_and_grad(x, dx, Xi * mask, p, s, e)
+    ref_loss += w_l1 * np.abs(Xi).sum()
+    ref_grad = ref_grad * mask + w_l1 * np.sign(Xi)
+    loss, grad, packed = nat.closure(dev(x), dev(dx), dev(Xi), dev(mask), lib, w_l1)
+    assert abs(float(loss) - ref_loss) < 2e-5 * abs(ref_loss)
+    assert rel(grad, ref_grad) < 2e-5
+    # the epilogue applied to the packed sums reproduces the fused result (multi-GPU path after the all-reduce)
+    loss2, grad2 = nat.step_epilogue(packed, dev(Xi), dev(mask), lib, w_l1)
+    assert abs(float(loss2) - float(loss)) <= 1e-6 * abs(float(loss)) and rel(grad2, grad) < 1e-6
+    # no mask, no L1
+    loss3, grad3, _ = nat.closure(dev(x), dev(dx), dev(Xi), None, lib, 0.0)
+    l3, g3 = O.mse_loss_and_grad(x, dx, Xi, p, s, e)
+    assert abs(float(loss3) - l3) < 2e-5 * abs(l3) and rel(grad3, g3) < 2e-5
+
+
+def test_sharded_step_single_process_and_graph(nat):
+    from sindy_b200.dist import ShardedTrainStep
+    rng = np.random.default_rng(5)
+    lib = nat.Library(3, 5)
+    n = 200_003
+    x, dx = dev(rng.uniform(-1, 1, (n, 3))), dev(rng.standard_normal((n, 3)))
+    Xi, mask = dev(rng.standard_normal((3, 56))), dev((rng.random((3, 56)) > 0.2).astype(np.float32))
+    eager = ShardedTrainStep(lib, x, dx)
+    l0, g0 = eager.step(Xi, mask, 0.01)
+    l0, g0 = float(l0), g0.clone()
+    graph = ShardedTrainStep(lib, x, dx, use_graph=True)
+    l1, g1 = graph.step(Xi, mask, 0.01)
+    assert float(l1) == l0 and torch.equal(g1, g0)
+    # sgd mode advances the static parameters in place; two steps == two manual updates
+    sgd = ShardedTrainStep(lib, x, dx, use_graph=True, sgd_lr=1e-3)
+    sgd.step(Xi, mask, 0.01)
+    sgd.step(None, None, 0.01)
+    Xi1 = Xi - 1e-3 * g0
+    _, g_b = eager.step(Xi1, mask, 0.01)
+    assert rel(sgd.xi, Xi1 - 1e-3 * g_b) < 1e-6
+
+
+def test_fused_variants_agree(nat):
+    """The A/B tuning variants of the headline kernel (SB_FUSED_VARIANT) are different schedules of the same sums."""
+    import subprocess, sys, os, json
+    code = (
+        "import sys, json, torch, numpy as np\n"
+        "sys.path[:0]=[%r, %r]\n"
+        "from sindy_b200 import native\n"
+        "g=torch.Generator(device='cuda').manual_seed(3)\n"
+        "x=torch.rand(123457,3,device='cuda',generator=g)*2-1; dx=torch.randn(123457,3,device='cuda',generator=g)\n"
+        "W=torch.randn(3,56,device='cuda',generator=g)\n"
+        "out=native.train_step(x,dx,W,native.Library(3,5),3)\n"
+        "print(json.dumps(out.cpu().tolist()))\n"
+    ) % (os.path.join(os.path.dirname(__file__), ".."), os.path.join(os.path.dirname(__file__), "..", "symmetry-ode-discovery_b200"))
+    res = []
+    for v in ("0", "1", "2", "3"):
+        env = dict(os.environ, SB_FUSED_VARIANT=v)
+        out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True).stdout
+        res.append(np.array(json.loads(out.strip().splitlines()[-1])))
+    for r in res[1:]:
+        assert np.abs(r - res[0]).max() / np.abs(res[0]).max() < 1e-6
+    assert np.array_equal(res[0], res[1])      # variants 0 and 1 differ only in synchronisation: identical bits

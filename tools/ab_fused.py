@@ -1,0 +1,26 @@
+"""A/B timing of the fused <3,5> kernel variants (SB_FUSED_VARIANT), one subprocess per variant."""
+import os, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+code = r'''
+import os, sys, torch
+sys.path[:0] = [%r, %r]
+from sindy_b200 import native
+lib = native.Library(3, 5)
+n = 10**8
+g = torch.Generator(device="cuda").manual_seed(1)
+x = torch.rand(n, 3, device="cuda", generator=g) * 2 - 1
+dx = torch.randn(n, 3, device="cuda", generator=g)
+W = torch.randn(3, 56, device="cuda", generator=g)
+out = torch.empty(lib.step_out_len(3), dtype=torch.float64, device="cuda")
+for _ in range(3): native.train_step(x, dx, W, lib, 3, out=out)
+torch.cuda.synchronize()
+ts = []
+for _ in range(15):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); native.train_step(x, dx, W, lib, 3, out=out); b.record(); torch.cuda.synchronize()
+    ts.append(a.elapsed_time(b))
+ts.sort()
+print("variant", os.environ.get("SB_FUSED_VARIANT"), "median %%.4f ms best %%.4f ms -> %%.2f Gsamples/s" %% (ts[7], ts[0], n / ts[7] / 1e6))
+''' % (ROOT, os.path.join(ROOT, "symmetry-ode-discovery_b200"))
+for v in sys.argv[1:] or ["0", "1", "2", "3"]:
+    subprocess.run([sys.executable, "-c", code], env=dict(os.environ, SB_FUSED_VARIANT=v))
