@@ -336,8 +336,8 @@ int tuning_variant() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("SB_FUSED_VARIANT");
-    v = e ? atoi(e) : 1;
-    if (v < 0 || v > 3) v = 1;
+    v = e ? atoi(e) : 3;  // measured on B200 (N = 1e8): 0: 1.450 ms, 1: 1.397, 2: 1.453, 3: 1.384
+    if (v < 0 || v > 3) v = 3;
   }
   return v;
 }
@@ -381,9 +381,9 @@ int launch_fused(const FusedArgs& a, void* ws, int64_t ws_bytes, cudaStream_t s)
   if constexpr (D == 3 && P == 5) {  // the headline shape carries the A/B variants
     switch (tuning_variant()) {
       case 0: return launch_fused_var<D, P, LEFT, 0>(a, ws, ws_bytes, s);
+      case 1: return launch_fused_var<D, P, LEFT, 1>(a, ws, ws_bytes, s);
       case 2: return launch_fused_var<D, P, LEFT, 2>(a, ws, ws_bytes, s);
-      case 3: return launch_fused_var<D, P, LEFT, 3>(a, ws, ws_bytes, s);
-      default: break;
+      default: return launch_fused_var<D, P, LEFT, 3>(a, ws, ws_bytes, s);
     }
   }
   return launch_fused_var<D, P, LEFT, 1>(a, ws, ws_bytes, s);
