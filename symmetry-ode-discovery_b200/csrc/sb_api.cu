@@ -103,8 +103,9 @@ int64_t sb_workspace_bytes(const sb_library* lib) {
   LibTab t;
   int s = build_table(lib, &t);
   if (s != SB_OK) return s;
-  int64_t a = generic_workspace_bytes(t), b = fused_workspace_bytes(t);
-  return a > b ? a : b;
+  int64_t a = generic_workspace_bytes(t), b = fused_workspace_bytes(t), c = moments_workspace_bytes(t);
+  if (b > a) a = b;
+  return c > a ? c : a;
 }
 
 int64_t sb_train_step_out_len(const sb_library* lib, uint32_t flags) {
@@ -191,9 +192,17 @@ int sb_train_step(const float* x, const float* dx, int64_t n, const sb_library* 
   SB_TRY(step_args_ok(x, dx, n, w, flags, out, ws));
   // the TMA-staged kernels need 16-byte aligned, contiguous x / dx
   const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dx)) & 15u) == 0;
-  if (n > 0 && aligned && fused_supported(t, flags))
-    return fused_train_step(x, dx, n, t, w, nullptr, flags, out, nullptr, ws, ws_bytes, (cudaStream_t)stream);
-  return generic_train_step(x, dx, n, t, w, flags, out, ws, ws_bytes, (cudaStream_t)stream);
+  cudaStream_t s = (cudaStream_t)stream;
+  const uint32_t rest = flags & ~SB_STEP_GRAM;   // sections served by the fused residual / ΘᵀẊ kernels
+  const bool gram = (flags & SB_STEP_GRAM) != 0;
+  const bool spec = n > 0 && aligned && (!rest || fused_supported(t, rest)) && (!gram || moments_supported(t));
+  if (!spec) return generic_train_step(x, dx, n, t, w, flags, out, ws, ws_bytes, s);
+  if (rest) SB_TRY(fused_train_step(x, dx, n, t, w, nullptr, rest, out, nullptr, ws, ws_bytes, s));
+  if (gram) {
+    double* g_out = out + 2 + ((flags & SB_STEP_GRAD) ? (int64_t)t.d * t.K : 0);
+    SB_TRY(moments_gram(x, n, t, g_out, rest ? nullptr : out, ws, ws_bytes, s));
+  }
+  return SB_OK;
 }
 
 int sb_closure(const float* x, const float* dx, int64_t n, const sb_library* lib, const float* xi, const float* mask,
@@ -231,7 +240,11 @@ int sb_step_epilogue(const double* packed, const sb_library* lib, const float* x
 const char* sb_train_step_variant(const sb_library* lib, uint32_t flags) {
   LibTab t;
   if (build_table(lib, &t) != SB_OK) return "unsupported";
-  return fused_supported(t, flags) ? fused_variant_name(t, flags) : "generic";
+  const uint32_t rest = flags & ~SB_STEP_GRAM;
+  const bool gram = (flags & SB_STEP_GRAM) != 0;
+  if ((rest && !fused_supported(t, rest)) || (gram && !moments_supported(t))) return "generic";
+  if (!rest) return "moments";
+  return fused_variant_name(t, rest);
 }
 
 int sb_rollout(const void* x0, int64_t n_ics, const sb_library* lib, const void* w, double dt,

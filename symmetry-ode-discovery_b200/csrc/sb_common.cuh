@@ -189,6 +189,12 @@ int fused_train_step(const float* x, const float* dx, int64_t n, const LibTab& t
                      uint32_t flags, double* out, const ClosureOut* co, void* ws, int64_t ws_bytes, cudaStream_t s);
 int64_t fused_workspace_bytes(const LibTab& t);
 
+// Gram ΘᵀΘ (K×K fp64) of a polynomial library from power sums; `header` (may be NULL) receives {0, n}
+bool moments_supported(const LibTab& t);
+int64_t moments_workspace_bytes(const LibTab& t);
+int moments_gram(const float* x, int64_t n, const LibTab& t, double* gram_out, double* header, void* ws,
+                 int64_t ws_bytes, cudaStream_t s);
+
 // rollout
 int rollout(const void* x0, int64_t n_ics, const LibTab& t, const void* w, double dt, int64_t n_steps,
             int64_t stride, int method, int dtype, int record_dx, void* x_out, void* dx_out, void* x_last,

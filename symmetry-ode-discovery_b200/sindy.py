@@ -114,6 +114,26 @@ class SINDyRegression(nn.Module):
         self.Xi = self._current_Xi()
         return ops.fused_mse(x, dx, self.Xi * self.mask, self.library)
 
+    def lie_reg_loss(self, z, generators, method='auto'):
+        """Linear Lie-derivative regulariser Σ_v Σ_n ‖J_h(z_n)(v z_n) − v h(z_n)‖² (the intended formula of the
+        reference's `train.py:503-507`), differentiable w.r.t. the parameters. 'gram': one moment pass + K×K
+        algebra (polynomial libraries); 'jvp': per-sample CUDA JVPs (any library); 'auto' picks."""
+        from sindy_b200 import symreg
+        self.Xi = self._current_Xi()
+        W = self.Xi * self.mask
+        poly = not (self.include_sine or self.include_exp)
+        if method == 'auto':
+            method = 'gram' if poly else 'jvp'
+        if method == 'gram':
+            key = tuple(float(q) for v in generators for q in torch.as_tensor(v).flatten().tolist())
+            if getattr(self, '_lie_key', None) != key:
+                self._lie_Ms = [symreg.lie_matrix(self.library, v) for v in generators]
+                self._lie_key = key
+            with torch.no_grad():
+                G = symreg.gram(z.reshape(-1, self.latent_dim), self.library)
+            return symreg.lie_loss_from_gram(G, W, generators, self._lie_Ms).to(W.dtype)
+        return symreg.lie_loss_per_sample(z.reshape(-1, self.latent_dim), W, generators, self.library)
+
     # ---- equivariance constraint (host-side setup) -------------------------------------------------
     def get_M_list(self):
         return [_lie_derivative_matrix(self.latent_dim, self.poly_order, Li) for Li in self.L_list]

@@ -56,8 +56,16 @@ class ShardedTrainStep:
     def __init__(self, lib: Library, x: Optional[torch.Tensor] = None, dx: Optional[torch.Tensor] = None,
                  flags: int = native.SB_STEP_LOSS | native.SB_STEP_GRAD, group=None,
                  local_sums: Optional[Callable[[torch.Tensor], torch.Tensor]] = None, use_graph: bool = False,
-                 sgd_lr: Optional[float] = None):
+                 sgd_lr: Optional[float] = None, sym_gens=None, w_sym: float = 0.0):
         self.lib, self.flags, self.group = lib, flags, group
+        # linear Lie-derivative regulariser (`train.py:503-507`) through the Gram matrix: see symreg.py
+        self.w_sym = float(w_sym)
+        self._sym = None
+        if sym_gens is not None and len(sym_gens) > 0:
+            from . import symreg
+            dev = x.device if x is not None else torch.device("cpu")
+            self._sym = (torch.stack([torch.as_tensor(v, dtype=torch.float64) for v in sym_gens]).to(dev),
+                         torch.stack([symreg.lie_matrix(lib, v) for v in sym_gens]).to(dev))
         self.x, self.dx = x, dx
         self._custom = local_sums
         self._use_graph = use_graph and local_sums is None
@@ -71,10 +79,29 @@ class ShardedTrainStep:
     def _buffers(self, dev):
         if self._bufs is None:
             d, K = self.lib.dim, self.lib.K
-            self._bufs = (torch.empty(self.lib.step_out_len(self.flags), dtype=torch.float64, device=dev),
-                          torch.empty((), dtype=torch.float32, device=dev),
+            n_step = self.lib.step_out_len(self.flags)
+            n_gram = self.lib.step_out_len(native.SB_STEP_GRAM) if self._sym is not None else 0
+            flat = torch.empty(n_step + n_gram, dtype=torch.float64, device=dev)  # ONE all-reduce covers both
+            self._flat = flat
+            self._gram = flat[n_step:] if n_gram else None
+            self._bufs = (flat[:n_step], torch.empty((), dtype=torch.float32, device=dev),
                           torch.empty(d, K, dtype=torch.float32, device=dev))
         return self._bufs
+
+    def _sym_terms(self, xi, mask):
+        """(Σ_v tr(A_v G A_vᵀ), its gradient w.r.t. Ξ) from the (all-reduced) Gram; A_v = W M_v − v W."""
+        K = self.lib.K
+        vs, Ms = self._sym
+        G = self._gram[2:].view(K, K)
+        W = (xi if mask is None else xi * mask).double()
+        A = W @ Ms - vs @ W                       # (V, d, K)
+        AG = A @ G
+        loss = (AG * A).sum()
+        gA = 2.0 * AG
+        gW = (gA @ Ms.transpose(1, 2)).sum(0) - (vs.transpose(1, 2) @ gA).sum(0)
+        if mask is not None:
+            gW = gW * mask
+        return loss, gW
 
     def local_sums(self, w: torch.Tensor) -> torch.Tensor:
         if self._custom is not None:
@@ -92,13 +119,19 @@ class ShardedTrainStep:
                 dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=self.group)
             return mse_from_sums(packed, self.lib, xi, mask, w_l1, xi if w_l1 != 0.0 else None)
         packed, loss, grad = self._buffers(self.x.device)
+        if self._sym is not None:   # second pass over x only: power sums -> Gram (data term and Gram share x in L2/HBM)
+            native.train_step(self.x, None, None, self.lib, native.SB_STEP_GRAM, out=self._gram)
         if world == 1:
             native.closure(self.x, self.dx, xi, mask, self.lib, w_l1, packed=packed, loss=loss, grad=grad)
         else:
             wm = xi if mask is None else xi * mask
             native.train_step(self.x, self.dx, wm, self.lib, self.flags, out=packed)
-            dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=self.group)
+            dist.all_reduce(self._flat, op=dist.ReduceOp.SUM, group=self.group)
             native.step_epilogue(packed, xi, mask, self.lib, w_l1, loss=loss, grad=grad)
+        if self._sym is not None:
+            ls, gs = self._sym_terms(xi, mask)
+            loss = loss + self.w_sym * ls.to(loss.dtype)
+            grad = grad + (self.w_sym * gs).to(grad.dtype)
         return loss, grad
 
     def _body(self, w_l1):
