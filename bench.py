@@ -180,6 +180,7 @@ def main():
     ap.add_argument("--cpu-samples", type=int, default=1_000_000, help="bounded sample of the CPU baseline")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-graph", action="store_true", help="do not capture the multi-GPU step in a CUDA graph")
+    ap.add_argument("--no-peer", action="store_true", help="multi-GPU: NCCL all-reduce instead of the in-kernel peer all-reduce")
     ap.add_argument("--skip-extras", action="store_true")
     args = ap.parse_args()
 
@@ -223,7 +224,9 @@ def main():
     #   1 GPU : pack Ξ⊙mask -> fused kernel (its last block writes loss and dL/dΞ, L1 term included) -> Ξ -= lr·grad
     #   N GPUs: the same with an all-reduce of the packed sums and a 1-launch epilogue, replayed as ONE CUDA graph
     use_graph = (world > 1) and not args.no_graph
-    stepper = ShardedTrainStep(lib, x, dx, flags=flags, use_graph=use_graph, sgd_lr=1e-3)
+    stepper = ShardedTrainStep(lib, x, dx, flags=flags, use_graph=use_graph, sgd_lr=1e-3, use_peer=not args.no_peer)
+    collective = "none" if world == 1 else ("in-kernel peer all-reduce over NVLink (sb_closure_peer)"
+                                            if stepper.peer is not None else "NCCL all-reduce + epilogue launch")
     stepper.step(Xi0, mask, w_l1)  # loads the static parameters (and captures the graph when enabled)
     stepper.xi.copy_(Xi0)
     kern_events = []
@@ -270,7 +273,8 @@ def main():
     clocks = sampler.stop() if sampler else None
     launches = native.kernel_launches() - launches0
     if use_graph:
-        launches = 3 * args.steps  # per replayed step: pack_w + fused kernel + epilogue (launched by the graph)
+        # per replayed step (launched by the graph): pack_w + fused kernel [+ epilogue when the all-reduce is NCCL]
+        launches = (2 if stepper.peer is not None else 3) * args.steps
     elapsed_ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
     if world > 1:
         dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
@@ -368,6 +372,7 @@ def main():
                    "samples_total": n_total, "samples_per_gpu": n_local, "symreg": "none",
                    "l2": "inputs (24 B/sample, %.2f GB per GPU) larger than L2; no flush" % (24 * n_local / 1e9),
                    "parallelism": f"sample-sharded x{world}, one all-reduce of {2 + D * K} fp64 sums per step",
+                   "collective": collective,
                    "cuda_graph": use_graph, "final_loss": final_loss},
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": 8,

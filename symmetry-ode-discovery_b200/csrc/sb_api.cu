@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "sb_common.cuh"
@@ -195,9 +196,15 @@ int sb_train_step(const float* x, const float* dx, int64_t n, const sb_library* 
   cudaStream_t s = (cudaStream_t)stream;
   const uint32_t rest = flags & ~SB_STEP_GRAM;   // sections served by the fused residual / ΘᵀẊ kernels
   const bool gram = (flags & SB_STEP_GRAM) != 0;
-  const bool spec = n > 0 && aligned && (!rest || fused_supported(t, rest)) && (!gram || moments_supported(t));
+  // The power-sum Gram rounds x^(α_k+α_l) once per sample instead of multiplying the two rounded columns; those
+  // rounding errors are unbiased and average out like eps/sqrt(n), but on small ill-conditioned batches they are
+  // amplified by cond(ΘᵀΘ). Below this sample count the exact-product generic rows are used (and are fast enough).
+  const char* env_min = getenv("SB_MOMENTS_MIN_SAMPLES");
+  const int64_t moments_min = env_min ? atoll(env_min) : (int64_t)1 << 20;
+  const bool spec = n > 0 && aligned && (!rest || fused_supported(t, rest)) &&
+                    (!gram || (moments_supported(t) && n >= moments_min));
   if (!spec) return generic_train_step(x, dx, n, t, w, flags, out, ws, ws_bytes, s);
-  if (rest) SB_TRY(fused_train_step(x, dx, n, t, w, nullptr, rest, out, nullptr, ws, ws_bytes, s));
+  if (rest) SB_TRY(fused_train_step(x, dx, n, t, w, nullptr, flags, out, nullptr, nullptr, ws, ws_bytes, s));  // GRAM bit only shifts the ΘᵀẊ offset
   if (gram) {
     double* g_out = out + 2 + ((flags & SB_STEP_GRAD) ? (int64_t)t.d * t.K : 0);
     SB_TRY(moments_gram(x, n, t, g_out, rest ? nullptr : out, ws, ws_bytes, s));
@@ -217,7 +224,7 @@ int sb_closure(const float* x, const float* dx, int64_t n, const sb_library* lib
   const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dx)) & 15u) == 0;
   if (n > 0 && aligned && fused_supported(t, flags)) {
     ClosureOut co{w_l1, loss_out, grad_out};
-    return fused_train_step(x, dx, n, t, xi, mask, flags, packed_out, &co, ws, ws_bytes, s);
+    return fused_train_step(x, dx, n, t, xi, mask, flags, packed_out, &co, nullptr, ws, ws_bytes, s);
   }
   // generic path: W = Ξ⊙mask in the workspace tail, residual rows, then the epilogue launch
   const int64_t need = generic_workspace_bytes(t);
@@ -226,6 +233,42 @@ int sb_closure(const float* x, const float* dx, int64_t n, const sb_library* lib
   SB_TRY(mask_mul(xi, mask, wm, t.d * t.K, s));
   SB_TRY(generic_train_step(x, dx, n, t, wm, flags, packed_out, ws, ws_bytes, s));
   return step_epilogue(packed_out, t, xi, mask, w_l1, loss_out, grad_out, s);
+}
+
+int64_t sb_peer_buffer_bytes(const sb_library* lib, int world) {
+  LibTab t;
+  int s = build_table(lib, &t);
+  if (s != SB_OK) return s;
+  if (world < 1 || world > SB_MAX_PEERS) return SB_ERR_INVALID;
+  return (int64_t)2 * world * ((int64_t)t.d * t.K + 2) * 8 + (int64_t)2 * world * 8;
+}
+
+int sb_closure_peer(const float* x, const float* dx, int64_t n, const sb_library* lib, const float* xi,
+                    const float* mask, double w_l1, double* packed_out, float* loss_out, float* grad_out, void* ws,
+                    int64_t ws_bytes, const void* const* peer_bufs, int world, int rank, uint32_t* epoch_dev,
+                    void* stream) {
+  LibTab t;
+  SB_TRY(build_table(lib, &t));
+  const uint32_t flags = SB_STEP_LOSS | SB_STEP_GRAD;
+  SB_TRY(step_args_ok(x, dx, n, xi, flags, packed_out, ws));
+  SB_TRY(check_ptr(loss_out, "loss_out")); SB_TRY(check_ptr(grad_out, "grad_out"));
+  SB_TRY(check_ptr(peer_bufs, "peer_bufs")); SB_TRY(check_ptr(epoch_dev, "epoch_dev"));
+  if (world < 2 || world > SB_MAX_PEERS || rank < 0 || rank >= world) {
+    set_error("bad world/rank %d/%d (2..%d ranks)", world, rank, SB_MAX_PEERS); return SB_ERR_INVALID;
+  }
+  const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dx)) & 15u) == 0;
+  if (!aligned || !fused_supported(t, flags)) {
+    set_error("sb_closure_peer needs a specialised library and 16-byte aligned inputs"); return SB_ERR_UNSUPPORTED;
+  }
+  PeerArgs pa;
+  pa.world = world; pa.rank = rank; pa.epoch = epoch_dev;
+  for (int r = 0; r < world; ++r) {
+    if (!peer_bufs[r]) { set_error("peer_bufs[%d] is NULL", r); return SB_ERR_INVALID; }
+    pa.buf[r] = reinterpret_cast<double*>(const_cast<void*>(peer_bufs[r]));
+  }
+  ClosureOut co{w_l1, loss_out, grad_out};
+  // n == 0 on a rank is legal (it still takes part in the exchange)
+  return fused_train_step(x, dx, n, t, xi, mask, flags, packed_out, &co, &pa, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 int sb_step_epilogue(const double* packed, const sb_library* lib, const float* xi, const float* mask, double w_l1,

@@ -180,13 +180,24 @@ int step_epilogue(const double* packed, const LibTab& t, const float* xi, const 
 // W = xi ⊙ mask into `dst` (d×K floats)
 int mask_mul(const float* xi, const float* mask, float* dst, int count, cudaStream_t s);
 
+// in-kernel all-reduce over peer-mapped symmetric buffers (one per rank; NVLink P2P). Layout of every buffer:
+// [2 parities][world slots][d*K + 2 doubles], then [2][world] 64-bit epoch flags. `epoch` is a local device
+// counter the kernel advances itself (CUDA-graph replay safe).
+struct PeerArgs {
+  int world = 0;
+  int rank = 0;
+  double* buf[SB_MAX_PEERS] = {};
+  unsigned int* epoch = nullptr;
+};
+
 // specialised (compile-time library, register-resident, TMA-staged) fused train step.
 // `w` is Ξ; `mask` (may be NULL) is multiplied in while packing W into the constant bank; `co` (may be NULL)
 // requests the closure epilogue inside the kernel's last block.
 bool fused_supported(const LibTab& t, uint32_t flags);
 const char* fused_variant_name(const LibTab& t, uint32_t flags);
 int fused_train_step(const float* x, const float* dx, int64_t n, const LibTab& t, const float* w, const float* mask,
-                     uint32_t flags, double* out, const ClosureOut* co, void* ws, int64_t ws_bytes, cudaStream_t s);
+                     uint32_t flags, double* out, const ClosureOut* co, const PeerArgs* peer, void* ws,
+                     int64_t ws_bytes, cudaStream_t s);
 int64_t fused_workspace_bytes(const LibTab& t);
 
 // Gram ΘᵀΘ (K×K fp64) of a polynomial library from power sums; `header` (may be NULL) receives {0, n}

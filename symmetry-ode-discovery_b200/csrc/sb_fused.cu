@@ -111,6 +111,8 @@ struct FusedArgs {
   double w_l1;
   float* loss_out;
   float* grad_out;
+  // optional in-kernel all-reduce over peer memory (NVLink P2P stores + flags): see the final phase
+  PeerArgs peer;
 };
 
 template <int D, int P, int LEFT, int VAR>
@@ -122,7 +124,7 @@ fused_step_kernel(FusedArgs a) {
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + C::kSmemData);
   uint64_t* empty = full + C::kStages;
   __shared__ float red[C::kWarps][C::NV];
-  __shared__ double fin[C::NV + 1];
+  __shared__ double fin[C::NV + 2];
   __shared__ int is_last;
 
   const int tid = threadIdx.x;
@@ -244,21 +246,68 @@ fused_step_kernel(FusedArgs a) {
     double v = 0.0;
     for (unsigned int b = 0; b < gridDim.x; ++b) v += a.partial[(int64_t)b * C::NV + e];
     fin[e] = v;
-    if (a.out) {
+  }
+  if (tid == 0) { fin[C::NV] = (double)a.n; *a.ticket = 0u; }
+  __syncthreads();
+
+  // ---- all-reduce across GPUs inside the kernel (no NCCL launch): each rank's last block pushes its NV+1 totals
+  // into slot [parity][rank] of EVERY rank's symmetric buffer with plain peer stores over NVLink, publishes a
+  // per-(parity, rank) epoch flag with a system-scope release store, waits for the flags of all ranks in its OWN
+  // buffer, and adds the slots in rank order (identical bits on every rank). Two parities suffice: a rank can run
+  // at most one step ahead, because finishing step e+1 needs every peer's flag e+1, which is only written after
+  // that peer has read the slots of step e.
+  if (a.peer.world > 1) {
+    constexpr int NVX = C::NV + 1;
+    const int world = a.peer.world, rank = a.peer.rank;
+    const unsigned long long epoch = (unsigned long long)(*a.peer.epoch) + 1ull;
+    const int par = (int)(epoch & 1ull);
+    for (int r = 0; r < world; ++r) {
+      double* dst = a.peer.buf[r] + (size_t)(par * world + rank) * NVX;
+      for (int e = tid; e < NVX; e += C::kThreads) dst[e] = fin[e];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < world) {
+      unsigned long long* f = reinterpret_cast<unsigned long long*>(a.peer.buf[tid] + (size_t)2 * world * NVX) +
+                              (par * world + rank);
+      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(epoch) : "memory");
+    }
+    if (tid < world) {
+      const unsigned long long* f =
+          reinterpret_cast<const unsigned long long*>(a.peer.buf[rank] + (size_t)2 * world * NVX) + (par * world + tid);
+      const long long t0 = clock64();
+      unsigned long long seen = 0;
+      do {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(f) : "memory");
+      } while (seen < epoch && (clock64() - t0) < 4000000000ll);   // ~2 s: never hang the GPU on a lost peer
+    }
+    __syncthreads();
+    const double* mine = a.peer.buf[rank] + (size_t)par * world * NVX;
+    for (int e = tid; e < NVX; e += C::kThreads) {
+      double v = 0.0;
+      for (int r = 0; r < world; ++r) v += mine[(size_t)r * NVX + e];
+      fin[e] = v;
+    }
+    if (tid == 0) *a.peer.epoch = (unsigned int)epoch;
+    __syncthreads();
+  }
+  const double n_total = fin[C::NV];
+
+  if (a.out) {
+    for (int e = tid; e < C::NV; e += C::kThreads) {
+      const double v = fin[e];
       if (e == C::NV - 1) {
-        if (a.write_header) { a.out[0] = v; a.out[1] = (double)a.n; }
+        if (a.write_header) { a.out[0] = v; a.out[1] = n_total; }
       } else {
         const int i = e / C::K, k = e % C::K;
         a.out[a.out_off + (a.out_transposed ? (int64_t)k * D + i : (int64_t)e)] = v;
       }
     }
   }
-  if (tid == 0) *a.ticket = 0u;
 
   // ---- closure epilogue (`train.py:663-664,680-683,689`) ----
   if (a.grad_out || a.loss_out) {
-    __syncthreads();
-    const double denom = (double)(a.n > 0 ? a.n : 1) * D;
+    const double denom = (n_total > 0.0 ? n_total : 1.0) * D;
     double l1 = 0.0;
     for (int e = tid; e < D * C::K; e += C::kThreads) {
       const float xi = a.xi[e];
@@ -374,7 +423,7 @@ int upload_w(const float* xi, const float* mask, cudaStream_t s) {
 
 template <int D, int P>
 int run_fused(const float* x, const float* dx, int64_t n, const float* w, const float* mask, uint32_t flags,
-              double* out, const ClosureOut* co, void* ws, int64_t ws_bytes, cudaStream_t s) {
+              double* out, const ClosureOut* co, const PeerArgs* peer, void* ws, int64_t ws_bytes, cudaStream_t s) {
   using C = Cfg<D, P>;
   FusedArgs a{};
   a.x = x; a.dx = dx; a.n = n; a.out = out;
@@ -384,12 +433,14 @@ int run_fused(const float* x, const float* dx, int64_t n, const float* w, const 
     if (st != SB_OK) return st;
     a.out_off = 2; a.out_transposed = 0; a.write_header = 1;
     if (co) { a.xi = w; a.mask = mask; a.w_l1 = co->w_l1; a.loss_out = co->loss; a.grad_out = co->grad; }
+    if (peer) a.peer = *peer;
     st = launch_fused<D, P, LEFT_RESIDUAL>(a, ws, ws_bytes, s);
     if (st != SB_OK) return st;
-    a.loss_out = nullptr; a.grad_out = nullptr;
+    a.loss_out = nullptr; a.grad_out = nullptr; a.peer = PeerArgs{};
   }
   if (flags & SB_STEP_B) {
-    a.out_off = 2 + ((flags & SB_STEP_GRAD) ? (int64_t)D * C::K : 0);
+    // the ΘᵀẊ section follows the (optional) gradient and Gram sections of the packed layout
+    a.out_off = 2 + ((flags & SB_STEP_GRAD) ? (int64_t)D * C::K : 0) + ((flags & SB_STEP_GRAM) ? (int64_t)C::K * C::K : 0);
     a.out_transposed = 1; a.write_header = resid ? 0 : 1;
     int st = launch_fused<D, P, LEFT_DX>(a, ws, ws_bytes, s);
     if (st != SB_OK) return st;
@@ -426,10 +477,11 @@ int64_t fused_workspace_bytes(const LibTab& t) {
 }
 
 int fused_train_step(const float* x, const float* dx, int64_t n, const LibTab& t, const float* w, const float* mask,
-                     uint32_t flags, double* out, const ClosureOut* co, void* ws, int64_t ws_bytes, cudaStream_t s) {
+                     uint32_t flags, double* out, const ClosureOut* co, const PeerArgs* peer, void* ws,
+                     int64_t ws_bytes, cudaStream_t s) {
 #define X(D, P)                                                  \
   if (t.d == D && t.n_poly == n_poly_terms(D, P))                \
-    return run_fused<D, P>(x, dx, n, w, mask, flags, out, co, ws, ws_bytes, s);
+    return run_fused<D, P>(x, dx, n, w, mask, flags, out, co, peer, ws, ws_bytes, s);
   SB_FUSED_SHAPES(X)
 #undef X
   set_error("no fused kernel for d=%d K=%d", t.d, t.K);

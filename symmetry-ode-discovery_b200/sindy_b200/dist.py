@@ -15,6 +15,7 @@ two device staging buffers on two copy streams while the kernel consumes the pre
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, Optional
 
 import torch
@@ -44,6 +45,37 @@ def mse_from_sums(packed: torch.Tensor, lib: Library, w: torch.Tensor, mask: Opt
     return loss, grad.to(w.dtype)
 
 
+class PeerExchange:
+    """Symmetric (peer-mapped) buffers for the in-kernel all-reduce of sb_closure_peer, allocated through
+    torch.distributed's symmetric memory (CUDA VMM + NVLink P2P). `available()` is False when the runtime cannot
+    provide it; the sharded step then uses an NCCL all-reduce + epilogue launch instead."""
+
+    def __init__(self, lib: Library, device: torch.device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        group = dist.group.WORLD if group is None else group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        n_bytes = native.peer_buffer_bytes(lib, self.world)
+        self.buf = symm_mem.empty((n_bytes + 7) // 8, dtype=torch.float64, device=device)
+        self.buf.zero_()
+        self.handle = symm_mem.rendezvous(self.buf, group)
+        self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=device)
+        torch.cuda.synchronize(device)
+        dist.barrier(group)       # every rank's buffer is zeroed before anybody's kernel may write into it
+
+    @staticmethod
+    def create(lib: Library, device: torch.device, group=None):
+        if os.environ.get("SB_NO_PEER", "0") == "1":
+            return None
+        try:
+            return PeerExchange(lib, device, group)
+        except Exception as exc:  # symmetric memory unsupported on this system / build
+            if os.environ.get("SB_PEER_DEBUG"):
+                print(f"[sindy_b200] peer exchange unavailable: {exc!r}")
+            return None
+
+
 class ShardedTrainStep:
     """loss, grad = step(Ξ, mask) over samples sharded across the ranks of `group` (or a single process).
 
@@ -56,7 +88,7 @@ class ShardedTrainStep:
     def __init__(self, lib: Library, x: Optional[torch.Tensor] = None, dx: Optional[torch.Tensor] = None,
                  flags: int = native.SB_STEP_LOSS | native.SB_STEP_GRAD, group=None,
                  local_sums: Optional[Callable[[torch.Tensor], torch.Tensor]] = None, use_graph: bool = False,
-                 sgd_lr: Optional[float] = None, sym_gens=None, w_sym: float = 0.0):
+                 sgd_lr: Optional[float] = None, sym_gens=None, w_sym: float = 0.0, use_peer: bool = True):
         self.lib, self.flags, self.group = lib, flags, group
         # linear Lie-derivative regulariser (`train.py:503-507`) through the Gram matrix: see symreg.py
         self.w_sym = float(w_sym)
@@ -74,6 +106,10 @@ class ShardedTrainStep:
         self._bufs = None
         self.xi = None      # static parameters (graph mode / sgd mode)
         self.mask = None
+        # in-kernel all-reduce over NVLink peer memory when several ranks share the step (no sym-reg Gram yet)
+        self.peer = None
+        if local_sums is None and x is not None and _world(group) > 1 and self._sym is None and use_peer:
+            self.peer = PeerExchange.create(lib, x.device, group)
 
     # -- pieces ----------------------------------------------------------------------------------------
     def _buffers(self, dev):
@@ -123,6 +159,9 @@ class ShardedTrainStep:
             native.train_step(self.x, None, None, self.lib, native.SB_STEP_GRAM, out=self._gram)
         if world == 1:
             native.closure(self.x, self.dx, xi, mask, self.lib, w_l1, packed=packed, loss=loss, grad=grad)
+        elif self.peer is not None:
+            native.closure_peer(self.x, self.dx, xi, mask, self.lib, self.peer.ptrs, self.peer.rank, self.peer.epoch,
+                                w_l1, packed=packed, loss=loss, grad=grad)
         else:
             wm = xi if mask is None else xi * mask
             native.train_step(self.x, self.dx, wm, self.lib, self.flags, out=packed)

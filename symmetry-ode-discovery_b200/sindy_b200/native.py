@@ -50,6 +50,10 @@ _SIGNATURES = {
                               c_void_p, c_int64, c_void_p]),
     "sb_closure": (c_int, [c_void_p, c_void_p, c_int64, POINTER(_CLibrary), c_void_p, c_void_p, c_double, c_void_p,
                            c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "sb_closure_peer": (c_int, [c_void_p, c_void_p, c_int64, POINTER(_CLibrary), c_void_p, c_void_p, c_double, c_void_p,
+                                c_void_p, c_void_p, c_void_p, c_int64, POINTER(c_void_p), c_int, c_int, c_void_p,
+                                c_void_p]),
+    "sb_peer_buffer_bytes": (c_int64, [POINTER(_CLibrary), c_int]),
     "sb_step_epilogue": (c_int, [c_void_p, POINTER(_CLibrary), c_void_p, c_void_p, c_double, c_void_p, c_void_p,
                                  c_void_p]),
     "sb_train_step_variant": (c_char_p, [POINTER(_CLibrary), c_uint32]),
@@ -296,6 +300,42 @@ def closure(x: torch.Tensor, dx: torch.Tensor, xi: torch.Tensor, mask: Optional[
         _check(load().sb_closure(xf.data_ptr(), dxf.data_ptr(), xf.shape[0], ctypes.byref(lib.c()), xi.data_ptr(),
                                  _ptr(mk), float(w_l1), packed.data_ptr(), loss.data_ptr(), grad.data_ptr(),
                                  ws.data_ptr(), ws.numel(), _stream(dev)), "sb_closure")
+    return loss, grad, packed
+
+
+def peer_buffer_bytes(lib: Library, world: int) -> int:
+    b = int(load().sb_peer_buffer_bytes(ctypes.byref(lib.c()), int(world)))
+    if b < 0:
+        _check(b, "sb_peer_buffer_bytes")
+    return b
+
+
+def closure_peer(x: torch.Tensor, dx: torch.Tensor, xi: torch.Tensor, mask: Optional[torch.Tensor], lib: Library,
+                 peer_ptrs, rank: int, epoch: torch.Tensor, w_l1: float = 0.0, packed: Optional[torch.Tensor] = None,
+                 loss: Optional[torch.Tensor] = None, grad: Optional[torch.Tensor] = None):
+    """closure() over samples sharded across GPUs with the all-reduce inside the kernel (peer stores over NVLink).
+    peer_ptrs: device pointers of every rank's symmetric buffer (index = rank); epoch: this rank's CUDA uint32
+    counter (zero before the first call). Returns the GLOBAL (loss, dL/dΞ, packed sums), identical on all ranks."""
+    xf = _flat(_f32c(x, "x"), lib.dim, "x")
+    dxf = _flat(_f32c(dx, "dx"), lib.dim, "dx")
+    xi = _f32c(xi, "xi")
+    mk = _f32c(mask, "mask") if mask is not None else None
+    dev = xf.device
+    d, K = lib.dim, lib.K
+    if packed is None:
+        packed = torch.empty(2 + d * K, dtype=torch.float64, device=dev)
+    if loss is None:
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+    if grad is None:
+        grad = torch.empty(d, K, dtype=torch.float32, device=dev)
+    world = len(peer_ptrs)
+    arr = (c_void_p * world)(*[int(p) for p in peer_ptrs])
+    ws = _workspace(lib, dev)
+    with torch.cuda.device(dev):
+        _check(load().sb_closure_peer(xf.data_ptr(), dxf.data_ptr(), xf.shape[0], ctypes.byref(lib.c()), xi.data_ptr(),
+                                      _ptr(mk), float(w_l1), packed.data_ptr(), loss.data_ptr(), grad.data_ptr(),
+                                      ws.data_ptr(), ws.numel(), arr, world, int(rank), epoch.data_ptr(),
+                                      _stream(dev)), "sb_closure_peer")
     return loss, grad, packed
 
 

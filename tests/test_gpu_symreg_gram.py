@@ -20,11 +20,12 @@ def rel(a, b):
 
 @pytest.mark.parametrize("d,p", [(2, 2), (2, 3), (3, 2), (3, 3), (3, 5)])
 @pytest.mark.parametrize("n", [2, 7, 5001, 400_003])
-def test_moment_gram_vs_oracle(d, p, n):
+def test_moment_gram_vs_oracle(d, p, n, monkeypatch):
     from sindy_b200 import native, symreg
     rng = np.random.default_rng(n + 10 * d + p)
     lib = native.Library(d, p)
     assert native.train_step_variant(lib, native.SB_STEP_GRAM) == "moments"
+    monkeypatch.setenv("SB_MOMENTS_MIN_SAMPLES", "0")     # force the power-sum kernel at test sizes
     x = rng.uniform(-1.2, 1.2, (n, d)).astype(np.float32)
     th = O.theta(x, p).astype(np.float64)
     G = symreg.gram(dev(x), lib)
@@ -66,8 +67,9 @@ def test_lie_matrix_is_the_symbolic_map(golden):
     np.testing.assert_allclose(symreg.lie_matrix(native.Library(2, 2), np.diag([2.0, 1.0])).numpy(), g["scaling2_M"], atol=1e-6)
 
 
-def test_sharded_step_with_symreg_matches_oracle():
+def test_sharded_step_with_symreg_matches_oracle(monkeypatch):
     from sindy_b200 import native
+    monkeypatch.setenv("SB_MOMENTS_MIN_SAMPLES", "0")
     from sindy_b200.dist import ShardedTrainStep
     rng = np.random.default_rng(2)
     d, p = 3, 5
