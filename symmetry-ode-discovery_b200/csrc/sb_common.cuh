@@ -139,6 +139,33 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// Transposed butterfly reduction of V per-lane values across the 32 lanes of a warp with ~V shuffles instead of
+// 5·V: at every step a lane keeps one half of its values and trades the other half with its partner. V must be a
+// multiple of 32. Afterwards v[0 .. V/32) of lane L hold the warp-wide sums of the original indices
+//   i + (L&16 ? V/2 : 0) + (L&8 ? V/4 : 0) + (L&4 ? V/8 : 0) + (L&2 ? V/16 : 0) + (L&1 ? V/32 : 0),  i < V/32.
+template <int V, int O = 16>
+__device__ __forceinline__ void warp_fold(float (&v)[V], int lane) {
+  static_assert(V % 32 == 0, "pad the value count to a multiple of 32");
+  if constexpr (O >= 1) {
+    constexpr int LIVE = V * O / 16;  // live values halve each step: V, V/2, ..., V/16
+    constexpr int H = LIVE / 2;
+    const bool up = (lane & O) != 0;
+    static_for<0, H>([&](auto ic) {
+      constexpr int i = ic;
+      const float lo = v[i], hi = v[i + H];
+      const float recv = __shfl_xor_sync(0xffffffffu, up ? lo : hi, O);
+      v[i] = (up ? hi : lo) + recv;
+    });
+    warp_fold<V, O / 2>(v, lane);
+  }
+}
+// original index of v[i] (i < V/32) held by `lane` after warp_fold<V>
+template <int V>
+__device__ __forceinline__ int warp_fold_index(int i, int lane) {
+  return i + ((lane & 16) ? V / 2 : 0) + ((lane & 8) ? V / 4 : 0) + ((lane & 4) ? V / 8 : 0) +
+         ((lane & 2) ? V / 16 : 0) + ((lane & 1) ? V / 32 : 0);
+}
+
 // Workspace header: one ticket counter (must be zero before the first call; every reducing kernel
 // resets it before exiting), padded to 256 bytes; partial sums follow.
 constexpr int64_t kWsHeaderBytes = 256;

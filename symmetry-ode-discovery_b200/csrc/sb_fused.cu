@@ -31,6 +31,10 @@ __constant__ float2 c_w2[kConstW / 2];
 // VAR selects a tuning variant (A/B-tested on the B200):
 //   bit 0: 1 = per-stage "empty" mbarriers (no __syncthreads in the tile loop), 0 = CTA barrier per tile
 //   bit 1: 1 = two partial sums per equation in the prediction, 0 = one
+//   bit 2: 1 = transposed-butterfly CTA reduction (~NV shuffles), 0 = one 5-step shuffle reduction per value
+//   bits 3-4: tile ring: 0 = 1024 samples x 4 stages, 1 = 2048 x 3, 2 = 4096 x 2, 3 = 2048 x 4
+//   bit 6: 1 = refill the stage consumed TWO tiles ago (its empty barrier has long completed), 0 = one tile ago
+//   bit 5: 1 = the next sample's x/dx are read from shared memory before the current sample is expanded
 template <int D, int P, int VAR = 1>
 struct Cfg {
   static constexpr int K = Poly<D, P>::K;
@@ -38,10 +42,14 @@ struct Cfg {
   static constexpr int NV = D * K + 1;       // values reduced per CTA (grad + loss)
   static constexpr int kThreads = 256;
   static constexpr int kWarps = kThreads / 32;
-  static constexpr int kTile = 1024;         // samples per stage
-  static constexpr int kStages = 4;
+  static constexpr int kTileCode = (VAR >> 3) & 3;        // samples per stage / ring depth
+  static constexpr int kTile = kTileCode == 0 ? 1024 : (kTileCode == 2 ? 4096 : 2048);
+  static constexpr int kStages = kTileCode == 0 ? 4 : (kTileCode == 1 ? 3 : (kTileCode == 2 ? 2 : 4));
+  static constexpr bool kPrefetch = (VAR & 32) != 0;
+  static constexpr int kLag = (VAR & 64) ? 2 : 1;          // the producer refills the stage consumed kLag tiles ago
   static constexpr bool kEmptyBarriers = (VAR & 1) != 0;
   static constexpr int kChains = (VAR & 2) ? 2 : 1;
+  static constexpr bool kFoldReduce = (VAR & 4) != 0;
   // accumulators dominate the register budget: D*K2*2 of them
   static constexpr int kMinBlocks = (D * K2 * 2 + K > 150) ? 1 : ((D * K2 * 2 + K > 40) ? 2 : 3);
   static constexpr size_t kSmemData = (size_t)kStages * 2 * kTile * D * sizeof(float);
@@ -167,12 +175,12 @@ fused_step_kernel(FusedArgs a) {
     const int stage = it % C::kStages;
     const uint32_t parity = (uint32_t)(it / C::kStages) & 1u;
     if constexpr (C::kEmptyBarriers) {
-      // refill the stage consumed one iteration ago: by now every warp has (almost surely) released it
-      if (tid == 0 && it > 0) {
-        const int64_t next = tile + (int64_t)(C::kStages - 1) * gridDim.x;
+      // refill the stage consumed kLag iterations ago: by now every warp has (almost surely) released it
+      if (tid == 0 && it >= C::kLag) {
+        const int64_t next = tile + (int64_t)(C::kStages - C::kLag) * gridDim.x;
         if (next < a.n_tiles) {
-          const int ps = (it - 1) % C::kStages;
-          mbar_wait(&empty[ps], (uint32_t)((it - 1) / C::kStages) & 1u);
+          const int ps = (it - C::kLag) % C::kStages;
+          mbar_wait(&empty[ps], (uint32_t)((it - C::kLag) / C::kStages) & 1u);
           issue(next, ps);
         }
       }
@@ -181,11 +189,24 @@ fused_step_kernel(FusedArgs a) {
     const float* sx = tiles + (size_t)stage * 2 * kTileFloats;
     const float* sd = sx + kTileFloats;
     const int cnt = tile_count(tile);
+    if constexpr (C::kPrefetch) {
+      float xn[D], dn[D];
+      if (tid < cnt) static_for<0, D>([&](auto q) { xn[q] = sx[tid * D + q]; dn[q] = sd[tid * D + q]; });
 #pragma unroll 1
-    for (int j = tid; j < cnt; j += C::kThreads) {
-      float xs[D], ds[D];
-      static_for<0, D>([&](auto q) { xs[q] = sx[j * D + q]; ds[q] = sd[j * D + q]; });
-      accumulate_sample<D, P, LEFT, VAR>(xs, ds, acc, lacc);
+      for (int j = tid; j < cnt; j += C::kThreads) {
+        float xs[D], ds[D];
+        static_for<0, D>([&](auto q) { xs[q] = xn[q]; ds[q] = dn[q]; });
+        const int jn = j + C::kThreads;
+        if (jn < cnt) static_for<0, D>([&](auto q) { xn[q] = sx[jn * D + q]; dn[q] = sd[jn * D + q]; });
+        accumulate_sample<D, P, LEFT, VAR>(xs, ds, acc, lacc);
+      }
+    } else {
+#pragma unroll 1
+      for (int j = tid; j < cnt; j += C::kThreads) {
+        float xs[D], ds[D];
+        static_for<0, D>([&](auto q) { xs[q] = sx[j * D + q]; ds[q] = sd[j * D + q]; });
+        accumulate_sample<D, P, LEFT, VAR>(xs, ds, acc, lacc);
+      }
     }
     if constexpr (C::kEmptyBarriers) {
       __syncwarp();
@@ -209,22 +230,41 @@ fused_step_kernel(FusedArgs a) {
     }
   }
 
-  // ---- CTA reduction: shuffles within the warp, fp64 across warps ----
-  static_for<0, D>([&](auto ic) {
-    constexpr int i = ic;
-    static_for<0, C::K2>([&](auto kc) {
-      constexpr int kk = kc;
-      const float vx = warp_sum(acc[i][kk].x);
-      const float vy = warp_sum(acc[i][kk].y);
-      if (lane == 0) {
-        red[wid][i * C::K + 2 * kk] = vx;
-        if (2 * kk + 1 < C::K) red[wid][i * C::K + 2 * kk + 1] = vy;
-      }
+  // ---- CTA reduction within the warp (fp32), fp64 across warps below ----
+  if constexpr (C::kFoldReduce) {
+    constexpr int V = ((C::NV + 31) / 32) * 32;
+    float v[V];
+    static_for<0, D>([&](auto ic) {
+      constexpr int i = ic;
+      static_for<0, C::K2>([&](auto kc) {
+        constexpr int kk = kc;
+        v[i * C::K + 2 * kk] = acc[i][kk].x;
+        if constexpr (2 * kk + 1 < C::K) v[i * C::K + 2 * kk + 1] = acc[i][kk].y;
+      });
     });
-  });
-  {
-    const float v = warp_sum(lacc);
-    if (lane == 0) red[wid][C::NV - 1] = v;
+    v[C::NV - 1] = lacc;
+    static_for<C::NV, V>([&](auto i) { v[i] = 0.f; });
+    warp_fold<V>(v, lane);
+    static_for<0, V / 32>([&](auto ic) {
+      constexpr int i = ic;
+      const int e = warp_fold_index<V>(i, lane);
+      if (e < C::NV) red[wid][e] = v[i];
+    });
+  } else {
+    static_for<0, D>([&](auto ic) {
+      constexpr int i = ic;
+      static_for<0, C::K2>([&](auto kc) {
+        constexpr int kk = kc;
+        const float vx = warp_sum(acc[i][kk].x);
+        const float vy = warp_sum(acc[i][kk].y);
+        if (lane == 0) {
+          red[wid][i * C::K + 2 * kk] = vx;
+          if (2 * kk + 1 < C::K) red[wid][i * C::K + 2 * kk + 1] = vy;
+        }
+      });
+    });
+    const float vl = warp_sum(lacc);
+    if (lane == 0) red[wid][C::NV - 1] = vl;
   }
   __syncthreads();
   double* mine = a.partial + (int64_t)blockIdx.x * C::NV;
@@ -241,11 +281,33 @@ fused_step_kernel(FusedArgs a) {
   if (!is_last) return;
   __threadfence();
 
-  // ---- ordered final reduction over CTAs ----
-  for (int e = tid; e < C::NV; e += C::kThreads) {
-    double v = 0.0;
-    for (unsigned int b = 0; b < gridDim.x; ++b) v += a.partial[(int64_t)b * C::NV + e];
-    fin[e] = v;
+  // ---- ordered final reduction over CTAs: warp w adds the partial rows b ≡ w (mod kWarps) with four independent
+  // accumulators (all loads of a lane are in flight together), then the kWarps sub-sums are added in warp order.
+  // The association is fixed by (gridDim, kWarps) only => run-to-run deterministic.
+  {
+    double* sub = reinterpret_cast<double*>(smem_raw);  // the tile ring is idle now: kWarps × NV doubles
+    for (int e0 = 0; e0 < C::NV; e0 += 32) {
+      const int e = e0 + lane;
+      if (e < C::NV) {
+        double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+        unsigned int b = wid;
+        for (; b + 3 * C::kWarps < gridDim.x; b += 4 * C::kWarps) {
+          v0 += a.partial[(int64_t)b * C::NV + e];
+          v1 += a.partial[(int64_t)(b + C::kWarps) * C::NV + e];
+          v2 += a.partial[(int64_t)(b + 2 * C::kWarps) * C::NV + e];
+          v3 += a.partial[(int64_t)(b + 3 * C::kWarps) * C::NV + e];
+        }
+        for (; b < gridDim.x; b += C::kWarps) v0 += a.partial[(int64_t)b * C::NV + e];
+        sub[wid * C::NV + e] = (v0 + v1) + (v2 + v3);
+      }
+    }
+    __syncthreads();
+    for (int e = tid; e < C::NV; e += C::kThreads) {
+      double v = 0.0;
+#pragma unroll
+      for (int wq = 0; wq < C::kWarps; ++wq) v += sub[wq * C::NV + e];
+      fin[e] = v;
+    }
   }
   if (tid == 0) { fin[C::NV] = (double)a.n; *a.ticket = 0u; }
   __syncthreads();
@@ -349,8 +411,10 @@ int tuning_variant() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("SB_FUSED_VARIANT");
-    v = e ? atoi(e) : 3;  // measured on B200 (N = 1e8): 0: 1.450 ms, 1: 1.397, 2: 1.453, 3: 1.384
-    if (v < 0 || v > 3) v = 3;
+    // A/B on B200 (closure at n = 1.94e7, graph replay): 3: 287.1 us, 7: 286.9, 11: 273.4, 19: 271.5 (worse tail at
+    // small n), 27: 279.2, 75: 273.2, 91: 281.1; at N = 1e8: 0: 1.450 ms, 1: 1.397, 2: 1.453, 3: 1.384
+    v = e ? atoi(e) : 11;
+    if (v < 0 || v > 127) v = 11;
   }
   return v;
 }
@@ -396,10 +460,13 @@ int launch_fused(const FusedArgs& a, void* ws, int64_t ws_bytes, cudaStream_t s)
       case 0: return launch_fused_var<D, P, LEFT, 0>(a, ws, ws_bytes, s);
       case 1: return launch_fused_var<D, P, LEFT, 1>(a, ws, ws_bytes, s);
       case 2: return launch_fused_var<D, P, LEFT, 2>(a, ws, ws_bytes, s);
-      default: return launch_fused_var<D, P, LEFT, 3>(a, ws, ws_bytes, s);
+      case 3: return launch_fused_var<D, P, LEFT, 3>(a, ws, ws_bytes, s);
+      case 7: return launch_fused_var<D, P, LEFT, 7>(a, ws, ws_bytes, s);
+      case 19: return launch_fused_var<D, P, LEFT, 19>(a, ws, ws_bytes, s);
+      default: return launch_fused_var<D, P, LEFT, 11>(a, ws, ws_bytes, s);
     }
   }
-  return launch_fused_var<D, P, LEFT, 1>(a, ws, ws_bytes, s);
+  return launch_fused_var<D, P, LEFT, 5>(a, ws, ws_bytes, s);  // small libraries: empty-barrier ring + folded reduction
 }
 
 // Ξ [⊙ mask] -> constant slot, one tiny launch on the stream (replaces a D2D cudaMemcpyToSymbolAsync + a mul)
