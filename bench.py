@@ -425,7 +425,32 @@ def extras(native, dev, peaks, fp32_peak):
         out[f"train_step_d{d}_p{p}_K{lib.K}"] = {"samples_per_s": n / (ms * 1e-3), "ms": ms, "hbm_gbs": gbs,
                                                  "hbm_frac": gbs / peaks["hbm_gbs"]}
         del x, dx
+    # the C5 step with the linear so(3) Lie-derivative regulariser (weight 0.1, `train.py:503-507`): closure kernel +
+    # power-sum Gram kernel (second pass over x) + K×K algebra, replayed as one CUDA graph; and the STLSQ data pass
+    from sindy_b200.dist import ShardedTrainStep
     lib = native.Library(D, P)
+    x = torch.rand(n, D, device=dev, generator=gen) * 2 - 1
+    dx = native.forward(x, truth_xi(dev), lib)
+    so3 = torch.zeros(3, 3, 3)
+    q = 0
+    for i in range(3):
+        for j in range(i):
+            so3[q, i, j], so3[q, j, i] = 1.0, -1.0
+            q += 1
+    W = torch.randn(D, K, device=dev, generator=gen)
+    st = ShardedTrainStep(lib, x, dx, sym_gens=list(so3), w_sym=0.1, use_graph=True, sgd_lr=1e-6)
+    st.step(W, torch.ones_like(W), 0.0)
+    ms = timed(lambda: st.step(None, None, 0.0))
+    flop_sym = FLOP_PER_SAMPLE + (9 + 65) + 2 * 286   # + leading powers, trailing table, one FMA per power sum
+    out["train_step_C5_with_so3_symreg"] = {"samples_per_s": n / (ms * 1e-3), "ms": ms, "flop_per_sample": flop_sym,
+                                            "fp32_tflops": flop_sym * n / (ms * 1e-3) / 1e12,
+                                            "fp32_frac": flop_sym * n / (ms * 1e-3) / 1e12 / fp32_peak,
+                                            "bytes_per_sample": 36}
+    o = torch.empty(lib.step_out_len(12), dtype=torch.float64, device=dev)
+    ms = timed(lambda: native.train_step(x, dx, None, lib, 12, out=o))
+    out["stlsq_data_pass_C5_gram_and_b"] = {"samples_per_s": n / (ms * 1e-3), "ms": ms,
+                                            "variant": native.train_step_variant(lib, 12)}
+    del x, dx
     x0 = torch.rand(10 ** 6, D, device=dev, generator=gen) * 2 - 1
     Xi = truth_xi(dev)
     ms = timed(lambda: native.rollout(x0, Xi, lib, 0.002, 2000, 10, "rk4"), reps=3)
