@@ -135,6 +135,7 @@ int sb_forward(const float* x, int64_t n, const sb_library* lib, const float* w,
   if (n < 0) { set_error("n=%lld < 0", (long long)n); return SB_ERR_INVALID; }
   if (n == 0) return SB_OK;
   SB_TRY(check_ptr(x, "x")); SB_TRY(check_ptr(w, "w")); SB_TRY(check_ptr(y, "y"));
+  if (fused_supported(t, SB_STEP_LOSS | SB_STEP_GRAD)) return fused_forward(x, n, t, w, y, (cudaStream_t)stream);
   return generic_forward(x, n, t, w, y, (cudaStream_t)stream);
 }
 
@@ -157,6 +158,13 @@ int sb_backward(const float* x, const float* gy, int64_t n, const sb_library* li
   if (n > 0) { SB_TRY(check_ptr(x, "x")); SB_TRY(check_ptr(gy, "gy")); }
   if (gx) SB_TRY(check_ptr(w, "w"));
   if (gw) SB_TRY(check_ptr(ws, "workspace"));
+  const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gy)) & 15u) == 0;
+  if (gw && n > 0 && aligned && fused_supported(t, SB_STEP_LOSS | SB_STEP_GRAD)) {
+    // dL/dW through the TMA-staged fused kernel (the cotangent plays the role of dx); gx, if wanted, per sample
+    SB_TRY(fused_weighted_sums(x, gy, n, t, gw, ws, ws_bytes, (cudaStream_t)stream));
+    if (!gx) return SB_OK;
+    return generic_backward(x, gy, n, t, w, nullptr, gx, ws, ws_bytes, (cudaStream_t)stream);
+  }
   return generic_backward(x, gy, n, t, w, gw, gx, ws, ws_bytes, (cudaStream_t)stream);
 }
 

@@ -226,6 +226,10 @@ int fused_train_step(const float* x, const float* dx, int64_t n, const LibTab& t
                      uint32_t flags, double* out, const ClosureOut* co, const PeerArgs* peer, void* ws,
                      int64_t ws_bytes, cudaStream_t s);
 int64_t fused_workspace_bytes(const LibTab& t);
+// specialised per-sample forward and dL/dW (cotangent-weighted feature sums) for the same libraries
+int fused_forward(const float* x, int64_t n, const LibTab& t, const float* w, float* y, cudaStream_t s);
+int fused_weighted_sums(const float* x, const float* g, int64_t n, const LibTab& t, double* out, void* ws,
+                        int64_t ws_bytes, cudaStream_t s);
 
 // Gram ΘᵀΘ (K×K fp64) of a polynomial library from power sums; `header` (may be NULL) receives {0, n}
 bool moments_supported(const LibTab& t);

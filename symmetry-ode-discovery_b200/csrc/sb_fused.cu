@@ -515,6 +515,54 @@ int run_fused(const float* x, const float* dx, int64_t n, const float* w, const 
   return SB_OK;
 }
 
+// h(x) = Θ(x)·Wᵀ per sample (`sindy.py:79-82`): Θ in registers, W pairs from the constant bank, packed FMAs.
+// 8·d bytes per sample (x in, y out) against (K−1−d) + 2Kd flop: HBM/FP32 balanced for K = 56, HBM-bound below.
+template <int D, int P>
+__global__ void __launch_bounds__(256) forward_spec_kernel(const float* __restrict__ x, int64_t n,
+                                                           float* __restrict__ y) {
+  using C = Cfg<D, P, 1>;
+  for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n; s += (int64_t)gridDim.x * blockDim.x) {
+    float xs[D], m[C::K];
+    static_for<0, D>([&](auto q) { xs[q] = __ldg(x + s * D + q); });
+    expand_poly<D, P>(xs, m);
+    float2 pred[D][2];
+    static_for<0, D>([&](auto i) { pred[i][0] = make_float2(0.f, 0.f); pred[i][1] = make_float2(0.f, 0.f); });
+    static_for<0, C::K2>([&](auto kc) {
+      constexpr int kk = kc;
+      const float2 m2 = make_float2(m[2 * kk], (2 * kk + 1 < C::K) ? m[2 * kk + 1] : 0.f);
+      static_for<0, D>([&](auto ic) {
+        constexpr int i = ic;
+        pred[i][kk % 2] = __ffma2_rn(c_w2[i * C::K2 + kk], m2, pred[i][kk % 2]);
+      });
+    });
+    static_for<0, D>([&](auto i) {
+      y[s * D + i] = (pred[i][0].x + pred[i][0].y) + (pred[i][1].x + pred[i][1].y);
+    });
+  }
+}
+
+template <int D, int P>
+int run_forward(const float* x, int64_t n, const float* w, float* y, cudaStream_t s) {
+  int st = upload_w<D, P>(w, nullptr, s);
+  if (st != SB_OK) return st;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  forward_spec_kernel<D, P><<<(unsigned)blocks, 256, 0, s>>>(x, n, y);
+  SB_LAUNCH_CHECK("forward_spec_kernel");
+  return SB_OK;
+}
+
+// out[i*K+k] = Σ_n g[n,i]·Θ_k(x_n) (d×K fp64): dL/dW of the forward for cotangent g (`train.py:689`) — the fused
+// kernel with the cotangent in the role of dx and no prediction.
+template <int D, int P>
+int run_weighted_sums(const float* x, const float* g, int64_t n, double* out, void* ws, int64_t ws_bytes,
+                      cudaStream_t s) {
+  FusedArgs a{};
+  a.x = x; a.dx = g; a.n = n; a.out = out;
+  a.out_off = 0; a.out_transposed = 0; a.write_header = 0;
+  return launch_fused<D, P, LEFT_DX>(a, ws, ws_bytes, s);
+}
+
 // the list of specialised libraries (polynomial only)
 #define SB_FUSED_SHAPES(X) X(2, 2) X(2, 3) X(3, 2) X(3, 3) X(3, 5)
 
@@ -537,6 +585,24 @@ const char* fused_variant_name(const LibTab& t, uint32_t flags) {
   SB_FUSED_SHAPES(X)
 #undef X
   return "generic";
+}
+
+int fused_forward(const float* x, int64_t n, const LibTab& t, const float* w, float* y, cudaStream_t s) {
+#define X(D, P) if (t.d == D && t.n_poly == n_poly_terms(D, P)) return run_forward<D, P>(x, n, w, y, s);
+  SB_FUSED_SHAPES(X)
+#undef X
+  set_error("no specialised forward for d=%d K=%d", t.d, t.K);
+  return SB_ERR_UNSUPPORTED;
+}
+
+int fused_weighted_sums(const float* x, const float* g, int64_t n, const LibTab& t, double* out, void* ws,
+                        int64_t ws_bytes, cudaStream_t s) {
+#define X(D, P) \
+  if (t.d == D && t.n_poly == n_poly_terms(D, P)) return run_weighted_sums<D, P>(x, g, n, out, ws, ws_bytes, s);
+  SB_FUSED_SHAPES(X)
+#undef X
+  set_error("no fused kernel for d=%d K=%d", t.d, t.K);
+  return SB_ERR_UNSUPPORTED;
 }
 
 int64_t fused_workspace_bytes(const LibTab& t) {

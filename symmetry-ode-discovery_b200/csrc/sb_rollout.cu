@@ -40,6 +40,22 @@ struct SpecRhs {
     constexpr int K = Poly<D, P>::K;
     T m[K];
     expand_poly<D, P>(x, m);
+    if constexpr (std::is_same<T, float>::value && K % 2 == 0) {
+      // fp32: packed fma.rn.f32x2 over adjacent columns, W pairs straight from the constant bank
+      const float2* w2 = reinterpret_cast<const float2*>(c_rw);
+      static_for<0, D>([&](auto ic) {
+        constexpr int i = ic;
+        float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
+        static_for<0, K / 2>([&](auto kc) {
+          constexpr int kk = kc;
+          const float2 m2 = make_float2(m[2 * kk], m[2 * kk + 1]);
+          if constexpr (kk % 2 == 0) s0 = __ffma2_rn(w2[i * (K / 2) + kk], m2, s0);
+          else s1 = __ffma2_rn(w2[i * (K / 2) + kk], m2, s1);
+        });
+        f[i] = (s0.x + s0.y) + (s1.x + s1.y);
+      });
+      return;
+    }
     const T* w = reinterpret_cast<const T*>(c_rw);
     static_for<0, D>([&](auto ic) {
       constexpr int i = ic;
