@@ -334,6 +334,27 @@ def main():
     h2d_bytes = host_step.h2d_bytes
     del xh, dxh
 
+    # ---- sharded RK4 rollout of the same config (10^6 ICs x 2000 steps, every 10th state stored): the ICs split
+    # over the ranks, no collective on the data path; time = max over ranks ----
+    rollout_sharded = None
+    if world > 1 and not args.skip_extras:
+        n_ics = 10 ** 6 // world + (1 if rank < 10 ** 6 % world else 0)
+        g2 = torch.Generator(device=dev).manual_seed(4321 + rank)
+        x0 = torch.rand(n_ics, D, device=dev, generator=g2) * 2 - 1
+        Xi_t = truth_xi(dev)
+        native.rollout(x0, Xi_t, lib, 0.002, 2000, 10, "rk4")
+        barrier()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        for _ in range(3):
+            native.rollout(x0, Xi_t, lib, 0.002, 2000, 10, "rk4")
+        r1.record()
+        torch.cuda.synchronize()
+        rt = torch.tensor([r0.elapsed_time(r1) / 3], device=dev)
+        dist.all_reduce(rt, op=dist.ReduceOp.MAX)
+        rollout_sharded = {"ic_steps_per_s": 2e9 / (float(rt) * 1e-3), "ms": float(rt), "ics_total": 10 ** 6,
+                           "steps": 2000, "dtype": "f32", "collective": "none (ICs are independent)"}
+
     if rank != 0:
         # every collective of this run has completed on all ranks (the last one is the e2e all-reduce); leave
         # without NCCL teardown: destroy_process_group() after CUDA-graph capture of collectives was seen to hang
@@ -382,6 +403,8 @@ def main():
         "roofline": roofline, "roofline_hbm": roofline_hbm,
     }
 
+    if rollout_sharded is not None:
+        result["extra"] = {"rk4_rollout_sharded": rollout_sharded}
     if world == 1:
         rate, cores, reps, med = cpu_closure_rate(args.cpu_samples)
         result["cpu_baseline"] = {

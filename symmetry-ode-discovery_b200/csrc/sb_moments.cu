@@ -10,7 +10,7 @@
 // Per sample: leading powers x0^a (a ≤ 2p) and the table T of the monomials of the trailing d−1 variables
 // (degree ≤ 2p, graded order, so "degree ≤ 2p−a" is a PREFIX of T); moment(a, j) += x0^a · T[j] as
 // fma.rn.f32x2 over adjacent j. The 286 accumulators of (3,5) do not fit one thread: the CTA is warp-specialised,
-// even warps own a ∈ [0,2), odd warps a ∈ [2,10], both sweep the same TMA-staged x tile (x is read once, 4·d
+// warps 0-3 own a ∈ [0,2), warps 4-7 a ∈ [2,10] (one warp of each per scheduler), both sweep the same TMA-staged x tile (x is read once, 4·d
 // bytes per sample). fp32 per thread, fp64 across threads, ordered last-block reduction (deterministic). A tiny
 // gather kernel then writes the K×K Gram from the moments.
 #include "sb_common.cuh"
@@ -187,15 +187,18 @@ __global__ void __launch_bounds__(kThreads, 1) moments_kernel(MomArgs a) {
   __syncthreads();
 
   if constexpr (C::kSplit) {
-    if ((wid & 1) == 0) {
+    // warps 0-3 take role 0, warps 4-7 role 1: every scheduler (warp id mod 4) hosts one warp of each role, so the
+    // unequal per-sample costs of the two roles add up identically on the four FMA pipes
+    constexpr int kHalf = kWarps / 2;
+    if (wid < kHalf) {
       float2 acc[C::R0::NPAIR];
       C::R0::zero(acc);
-      sweep<typename C::R0, D>(a, tiles, full, empty, wid >> 1, kWarps / 2, lane, tid == 0, acc);
+      sweep<typename C::R0, D>(a, tiles, full, empty, wid, kHalf, lane, tid == 0, acc);
       C::R0::reduce(acc, red[wid], lane);
     } else {
       float2 acc[C::R1::NPAIR];
       C::R1::zero(acc);
-      sweep<typename C::R1, D>(a, tiles, full, empty, wid >> 1, kWarps / 2, lane, false, acc);
+      sweep<typename C::R1, D>(a, tiles, full, empty, wid - kHalf, kHalf, lane, false, acc);
       C::R1::reduce(acc, red[wid], lane);
     }
   } else {
@@ -213,7 +216,7 @@ __global__ void __launch_bounds__(kThreads, 1) moments_kernel(MomArgs a) {
       const int role = (e < C::R0::NOUT) ? 0 : 1;
       const int local = role ? e - C::R0::NOUT : e;
 #pragma unroll
-      for (int wq = 0; wq < kWarps / 2; ++wq) v += (double)red[2 * wq + role][local];
+      for (int wq = 0; wq < kWarps / 2; ++wq) v += (double)red[role * (kWarps / 2) + wq][local];
     } else {
 #pragma unroll
       for (int wq = 0; wq < kWarps; ++wq) v += (double)red[wq][e];
