@@ -341,8 +341,44 @@ def gen_lbfgs():
     save("lbfgs", **out)
 
 
+def gen_adam():
+    """a3/a6 through the Adam loop: the reference's train_SIGED (data-space branch: MSE + w_sym_reg*symmreg_i + L1,
+    thresholding every st_freq epochs) with the frozen stand-in autoencoder/generator."""
+    import train as ref_train
+    import wandb
+    wandb.init(mode="disabled")
+    out = {}
+    ae, gen = standins.make_standins(seed=1, input_dim=2, n_comps=2, hidden=16)
+    out.update({f"ae_{k}": v for k, v in ae.state_dict().items()})
+    out["gen_basis"] = torch.stack(gen.get_full_basis_list())
+    rng = np.random.default_rng(21)
+    n = 512
+    x = rng.uniform(0.3, 1.2, size=(n, 2)).astype(np.float32)
+    th = make_reg(2, 2, False, False).eval_Theta_at(torch.from_numpy(x)).numpy().astype(np.float64)
+    dx = (th @ sindy_truth["growth"].T + 0.01 * rng.standard_normal((n, 2))).astype(np.float32)
+    xt, dxt = torch.from_numpy(x), torch.from_numpy(dx)
+    loader = [(xt[i:i + 128], dxt[i:i + 128]) for i in range(0, n, 128)]
+    reg = make_reg(2, 2, False, False, seed=5)
+    reg.Xi.data = 0.2 * reg.Xi.data
+    out["init_Xi"] = reg.Xi.detach().clone()
+    cwd = os.getcwd()
+    os.chdir("/tmp")
+    try:
+        ref_train.train_SIGED(
+            train_loader=loader, test_loader=loader, num_epochs=6, device="cpu", log_interval=1000,
+            save_interval=100000, save_dir="golden_tmp", autoencoder=ae, discriminator=torch.nn.Identity(), generator=gen,
+            lr_ae=1e-3, lr_d=1e-3, lr_g=1e-3, w_recon=0.0, w_gan=0.0, w_reg_norm=0.0, w_reg_ortho=0.0,
+            w_reg_closure=0.0, use_original_x=False, gan_st_freq=5, gan_st_thres=0.3, ae_arch='mlp', regressor=reg,
+            use_latent=False, lr_sindy=2e-2, w_sindy_z=0.0, w_sindy_x=1.0, sindy_reg_type='l1', w_sindy_reg=1e-3,
+            w_sym_reg=0.05, st_freq=3, threshold=0.02, int_t=0.1, int_dt=0.01, print_eq=False, print_li=False)
+    finally:
+        os.chdir(cwd)
+    out.update({"x": x, "dx": dx, "final_Xi": reg.Xi.detach(), "final_mask": reg.mask})
+    save("adam", **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["model", "jvp", "stlsq", "wsindy", "rollout", "symmreg", "lbfgs"]
+    which = sys.argv[1:] or ["model", "jvp", "stlsq", "wsindy", "rollout", "symmreg", "lbfgs", "adam"]
     for w in which:
         globals()["gen_" + w]()

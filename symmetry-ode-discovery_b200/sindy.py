@@ -114,6 +114,25 @@ class SINDyRegression(nn.Module):
         self.Xi = self._current_Xi()
         return ops.fused_mse(x, dx, self.Xi * self.mask, self.library)
 
+    def sufficient_statistics(self, x, dx):
+        """One pass over (x, dx): everything the MSE objective needs, as fp64 tensors (G = ΘᵀΘ, b = ΘᵀẊ, Σẋ², n).
+        The MSE (and the linear Lie-derivative regulariser) are exact quadratics in Ξ given these."""
+        lib = self.library
+        flags = native.SB_STEP_GRAM | native.SB_STEP_B
+        with torch.no_grad():
+            parts = native.unpack_step(native.train_step(x, dx, None, lib, flags), lib, flags)
+            yy = (dx.reshape(-1, lib.dim).double() ** 2).sum()
+        return {"G": parts["gram"], "b": parts["b"], "yy": yy, "n": float(parts["n"])}
+
+    def mse_loss_from_statistics(self, stats):
+        """mean((Θ(x)(Ξ⊙mask)ᵀ − dx)²) = (tr(W G Wᵀ) − 2 tr(W b) + Σẋ²)/(n·d) with NO pass over the data; differentiable
+        w.r.t. the parameters (fp64 algebra on K×K, result cast to the parameter dtype). One data pass per FIT instead
+        of one per closure evaluation (`train.py:693-695` makes up to 20 per epoch)."""
+        self.Xi = self._current_Xi()
+        W = (self.Xi * self.mask).double()
+        quad = ((W @ stats["G"]) * W).sum() - 2.0 * (W * stats["b"].T).sum() + stats["yy"]
+        return (quad / (stats["n"] * self.latent_dim)).to(self.Xi.dtype)
+
     def lie_reg_loss(self, z, generators, method='auto'):
         """Linear Lie-derivative regulariser Σ_v Σ_n ‖J_h(z_n)(v z_n) − v h(z_n)‖² (the intended formula of the
         reference's `train.py:503-507`), differentiable w.r.t. the parameters. 'gram': one moment pass + K×K

@@ -128,6 +128,11 @@ def train_SIGED_lbfgs(
     autoencoder.eval()
     generator.eval()
     mse = torch.nn.MSELoss()
+    # cached_gram=True (extension): the batch is fixed for the whole fit (`train.py:626-629`), so the
+    # MSE is an exact quadratic in Ξ given G = ΘᵀΘ, b = ΘᵀẊ, Σẋ²: ONE data pass for the fit, every closure is K×K algebra
+    stats = None
+    if kwargs.get('cached_gram') and not use_latent:
+        stats = regressor.sufficient_statistics(x, dx)
 
     def data_loss(losses):
         if use_latent:
@@ -138,7 +143,10 @@ def train_SIGED_lbfgs(
             loss_z, loss_x = mse(dz_pred, dz), mse(dx_pred, dx)
             losses['loss_sindy_z'], losses['loss_sindy_x'] = loss_z.detach(), loss_x.detach()
             return w_sindy_z * loss_z + w_sindy_x * loss_x
-        loss_x = regressor.mse_loss(x, dx)          # fused: value and dL/dΞ from one pass
+        if stats is not None:
+            loss_x = regressor.mse_loss_from_statistics(stats)   # closure-free: K×K algebra, no data pass
+        else:
+            loss_x = regressor.mse_loss(x, dx)      # fused: value and dL/dΞ from one pass
         losses['loss_sindy_x'] = loss_x.detach()
         loss = w_sindy_x * loss_x
         if w_sym_reg > 0.0:
@@ -205,7 +213,7 @@ def train_SIGED(
     symm_loss = make_symmreg_pttrain(autoencoder, generator)
     for epoch in range(num_epochs):
         running = {'loss_sindy_x': [], 'loss_sym_reg': [], 'loss_sindy_reg': []}
-        autoencoder.train(); generator.train()
+        regressor.train()   # the autoencoder / generator stay in eval mode (the reference's .train() calls are commented out)
         for x, dx in train_loader:
             x, dx = x.to(device), dx.to(device)
             loss_x = regressor.mse_loss(x, dx)
