@@ -7,10 +7,10 @@
 Workload (BASELINE.json configs[4], SURVEY.md §8d "C5"): synthetic library fit, N = 1e8 samples in total,
 d = 3, polynomial degree 5 (K = 56), X ~ U(-1,1)^3 generated on the device (seed 1234 + rank),
 dX = Θ(X)Ξ*ᵀ + 0.01·randn with the Lorenz-form Ξ*, Ξ initialised randn(3,56) with torch.manual_seed(0).
-A "step" is one closure evaluation of the LBFGS loop (`train.py:645-690`): loss = MSE + w·‖Ξ‖₁ and dL/dΞ over
-ALL samples (one fused kernel per rank + one all-reduce of the 170 packed fp64 sums + a tiny epilogue), followed
-by a parameter update so that no step can reuse the previous one. Samples are sharded over the ranks (total
-work fixed: strong scaling). Inputs (2.4 GB) exceed the 126 MB L2, so no flush is needed between steps.
+A "step" is one iteration of the reference's Adam loop without sym-reg (`train.py:512-530`): loss = MSE + w·‖Ξ‖₁
+and dL/dΞ over ALL samples, then the Adam update of Ξ — ONE launch of the fused kernel per rank (sb_fit_step): its
+last block all-reduces the 170 packed fp64 sums over NVLink peer memory, writes loss and gradient, advances Ξ and
+packs the next Ξ⊙mask into the constant bank. Samples are sharded over the ranks (total work fixed: strong scaling). Inputs (2.4 GB) exceed the 126 MB L2, so no flush is needed between steps.
 
 Printed JSON (rank 0, one line): value = whole-job samples/s with inputs resident in HBM; e2e = the same step
 through HostStreamedStep with x/dx in pinned HOST memory (H2D of every sample inside the timed region) and a
@@ -195,7 +195,7 @@ def main():
 
     import torch.distributed as dist
     from sindy_b200 import native
-    from sindy_b200.dist import HostStreamedStep, ShardedTrainStep, mse_from_sums
+    from sindy_b200.dist import FitStepper, HostStreamedStep, ShardedTrainStep, mse_from_sums
 
     native.load()  # fails loudly if the CUDA library is missing: there is no fallback path
     torch.cuda.set_device(local_rank)
@@ -220,35 +220,48 @@ def main():
     flags = native.SB_STEP_LOSS | native.SB_STEP_GRAD
     variant = native.train_step_variant(lib, flags)
 
-    # One step = one closure evaluation + the parameter update, all on the device:
-    #   1 GPU : pack Ξ⊙mask -> fused kernel (its last block writes loss and dL/dΞ, L1 term included) -> Ξ -= lr·grad
-    #   N GPUs: the same with an all-reduce of the packed sums and a 1-launch epilogue, replayed as ONE CUDA graph
-    use_graph = (world > 1) and not args.no_graph
-    stepper = ShardedTrainStep(lib, x, dx, flags=flags, use_graph=use_graph, sgd_lr=1e-3, use_peer=not args.no_peer)
-    collective = "none" if world == 1 else ("in-kernel peer all-reduce over NVLink (sb_closure_peer)"
-                                            if stepper.peer is not None else "NCCL all-reduce + epilogue launch")
-    stepper.step(Xi0, mask, w_l1)  # loads the static parameters (and captures the graph when enabled)
-    stepper.xi.copy_(Xi0)
+    # One step = one iteration of the reference's Adam loop without sym-reg (`train.py:512-530`): forward, MSE + L1,
+    # backward, optimizer.step() — ONE launch of the fused kernel per rank (sb_fit_step): its last block all-reduces
+    # the sums over NVLink peer memory (N > 1), evaluates loss and gradient, applies Adam to Ξ in place and packs Ξ⊙mask
+    # into the constant bank for the next launch. Replayed as a CUDA graph. `--no-peer`: the 3-launch NCCL path.
+    legacy = args.no_peer or args.no_graph
     kern_events = []
+    if not legacy:
+        stepper = FitStepper(lib, x, dx, "adam", lr=1e-3, w_l1=w_l1, use_graph=True)
+        stepper.load(Xi0, mask)
+        collective = "none" if world == 1 else "in-kernel peer all-reduce over NVLink (sb_fit_step)"
+        launches_per_step = 1
+        use_graph = True
 
-    def one_step(record=False):
-        if record and not use_graph:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            packed, loss_t, grad_t = stepper._buffers(dev)
-            if world == 1:
-                native.closure(x, dx, stepper.xi, stepper.mask, lib, w_l1, packed=packed, loss=loss_t, grad=grad_t)
-                e1.record()
-            else:
-                native.train_step(x, dx, stepper.xi * stepper.mask, lib, flags, out=packed)
-                e1.record()
-                dist.all_reduce(packed)
-                native.step_epilogue(packed, stepper.xi, stepper.mask, lib, w_l1, loss=loss_t, grad=grad_t)
-            kern_events.append((e0, e1))
-            stepper.xi.add_(grad_t, alpha=-1e-3)
+        def one_step(record=False):
+            return stepper.step()
+    else:
+        use_graph = (world > 1) and not args.no_graph
+        stepper = ShardedTrainStep(lib, x, dx, flags=flags, use_graph=use_graph, sgd_lr=1e-3, use_peer=not args.no_peer)
+        collective = "none" if world == 1 else ("in-kernel peer all-reduce over NVLink (sb_closure_peer)"
+                                                if stepper.peer is not None else "NCCL all-reduce + epilogue launch")
+        stepper.step(Xi0, mask, w_l1)  # loads the static parameters (and captures the graph when enabled)
+        stepper.xi.copy_(Xi0)
+        launches_per_step = 2 if (world == 1 or stepper.peer is not None) else 3
+
+        def one_step(record=False):
+            if record and not use_graph:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                packed, loss_t, grad_t = stepper._buffers(dev)
+                if world == 1:
+                    native.closure(x, dx, stepper.xi, stepper.mask, lib, w_l1, packed=packed, loss=loss_t, grad=grad_t)
+                    e1.record()
+                else:
+                    native.train_step(x, dx, stepper.xi * stepper.mask, lib, flags, out=packed)
+                    e1.record()
+                    dist.all_reduce(packed)
+                    native.step_epilogue(packed, stepper.xi, stepper.mask, lib, w_l1, loss=loss_t, grad=grad_t)
+                kern_events.append((e0, e1))
+                stepper.xi.add_(grad_t, alpha=-1e-3)
+                return loss_t
+            loss_t, _ = stepper.step(None, None, w_l1)
             return loss_t
-        loss_t, _ = stepper.step(None, None, w_l1)
-        return loss_t
 
     def barrier():
         if world > 1:
@@ -272,9 +285,8 @@ def main():
     barrier()
     clocks = sampler.stop() if sampler else None
     launches = native.kernel_launches() - launches0
-    if use_graph:
-        # per replayed step (launched by the graph): pack_w + fused kernel [+ epilogue when the all-reduce is NCCL]
-        launches = (2 if stepper.peer is not None else 3) * args.steps
+    if use_graph:   # kernels launched by the replayed graph are not seen by the library's launch counter
+        launches = launches_per_step * args.steps
     elapsed_ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
     if world > 1:
         dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
@@ -283,7 +295,11 @@ def main():
     final_loss = float(loss)
 
     # ---- kernel-only duration (roofline numerator) ----
-    if kern_events:
+    if not legacy:
+        kern_ms = elapsed_ms / args.steps
+        kern_how = ("CUDA events around the K timed steps: a step IS one launch of the fused kernel (sample loop, "
+                    "reductions, peer all-reduce, loss/gradient, Adam update), so launch gaps are included")
+    elif kern_events:
         kern_ms = sum(a.elapsed_time(b) for a, b in kern_events) / len(kern_events)
         kern_how = "CUDA events around the library call (pack_w + fused kernel) inside every timed step"
     else:
@@ -390,6 +406,8 @@ def main():
         "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "C5 synthetic library fit: d=3, poly degree 5 (K=56), MSE+L1 closure, loss+grad",
+                   "step": ("one Adam iteration (train.py:512-530): loss, gradient, update in ONE launch (sb_fit_step)"
+                            if not legacy else "closure + SGD update (pack_w, fused kernel[, all-reduce, epilogue], axpy)"),
                    "samples_total": n_total, "samples_per_gpu": n_local, "symreg": "none",
                    "l2": "inputs (24 B/sample, %.2f GB per GPU) larger than L2; no flush" % (24 * n_local / 1e9),
                    "parallelism": f"sample-sharded x{world}, one all-reduce of {2 + D * K} fp64 sums per step",

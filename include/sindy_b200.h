@@ -155,6 +155,42 @@ int sb_closure_peer(const float* x, const float* dx, int64_t n, const sb_library
                     uint32_t* epoch_dev, void* stream);
 int64_t sb_peer_buffer_bytes(const sb_library* lib, int world);
 
+/* One whole iteration of the reference's Adam loop without sym-reg (`train.py:512-530`: forward, MSELoss, L1,
+ * backward, optimizer.step()) as ONE kernel launch for the specialised libraries: the last block of the fused kernel
+ * evaluates loss = w_mse·MSE + w_l1·‖Ξ‖₁ and its gradient (as sb_closure, at the parameters BEFORE the update), applies
+ * the optimiser update to `xi` in place and packs the new Ξ⊙mask into the constant bank for the next call.
+ *   SB_OPT_SGD : Ξ ← Ξ − lr·g
+ *   SB_OPT_ADAM: torch.optim.Adam (no weight decay, no amsgrad) in fp32 with the same operation order:
+ *                m ← lerp(m, g, 1−β1); v ← β2·v + (1−β2)·g²; Ξ ← Ξ − lr/(1−β1ᵗ) · m / (√v/√(1−β2ᵗ) + eps)
+ * opt_state (Adam only): 2·d·K floats [m | v] followed by one uint32 step counter t (all zero before the first step;
+ * the kernel advances t). call_flags: SB_FIT_W_RESIDENT promises that the constant bank still holds Ξ⊙mask of THESE
+ * parameters — true right after sb_load_w or after the previous sb_fit_step on the same device and stream, provided
+ * no other call of this library that takes a coefficient matrix ran in between and xi/mask were not modified by the
+ * caller; without the flag the call packs Ξ⊙mask first (one more launch). peer_bufs/world/rank/epoch_dev as in
+ * sb_closure_peer (world ≤ 1: single GPU, peer_bufs/epoch_dev may be NULL): every rank applies the identical update to
+ * its replica of Ξ from the identical all-reduced gradient. Libraries without a specialised kernel, or misaligned
+ * inputs: SB_ERR_UNSUPPORTED (use sb_closure + the framework's optimiser). */
+#define SB_OPT_NONE 0
+#define SB_OPT_SGD 1
+#define SB_OPT_ADAM 2
+#define SB_FIT_W_RESIDENT 1u
+typedef struct {
+  int32_t kind;  /* SB_OPT_SGD / SB_OPT_ADAM */
+  float lr;
+  float beta1;   /* Adam; torch defaults 0.9, 0.999, 1e-8 */
+  float beta2;
+  float eps;
+  float w_mse;   /* w_sindy_x */
+  float w_l1;    /* w_sindy_reg */
+} sb_fit_options;
+int sb_fit_step(const float* x, const float* dx, int64_t n, const sb_library* lib, float* xi, const float* mask,
+                const sb_fit_options* opt, float* opt_state, double* packed_out, float* loss_out, float* grad_out,
+                void* workspace, int64_t workspace_bytes, const void* const* peer_bufs, int world, int rank,
+                uint32_t* epoch_dev, uint32_t call_flags, void* stream);
+/* Ξ⊙mask (mask may be NULL) into the constant bank of the specialised kernels: makes SB_FIT_W_RESIDENT true for the
+ * next sb_fit_step after the caller changed xi or mask (e.g. `set_threshold`, `sindy.py:192-195`). */
+int sb_load_w(const sb_library* lib, const float* xi, const float* mask, void* stream);
+
 /* The same epilogue applied to packed sums that were combined across GPUs (all-reduce(sum) of
  * sb_train_step's output): loss_out / grad_out as in sb_closure (either may be NULL). */
 int sb_step_epilogue(const double* packed, const sb_library* lib, const float* xi, const float* mask,
@@ -184,6 +220,12 @@ int sb_rollout(const void* x0, int64_t n_ics, const sb_library* lib, const void*
  * operation order. G (n_traj×n_test×K) and b (n_traj×n_test×d) are fp64. */
 int sb_wsindy_integrals(const float* x, int64_t n_traj, int64_t T, const sb_library* lib, float dt,
                         double t_max, int n_test, double* G, double* b, void* stream);
+
+/* Debug/profiling aid: while dev_buf (device memory, 16 uint64 per CTA, at least 16·592 words) is set, every fused
+ * kernel launched afterwards records %globaltimer stamps of its phases per CTA: 0 entry, 1 first tile landed, 2 end of
+ * the sample loop, 3 partial written + ticket taken, and for the last block 4 totals ready, 5 after the peer exchange,
+ * 6 end of the epilogue, 7 = SM id, 8 partial rows staged in shared memory, 9 rows summed. NULL switches it off (default). Not thread-safe; tools/trace_fused.py reads it. */
+void sb_debug_trace(void* dev_buf);
 
 /* FP32 FMA-pipe peak microbenchmark used for the roofline denominator (not in MEASURED_PEAKS.json):
  * variant 0 = scalar FFMA, 1 = packed FFMA2 (fma.rn.f32x2), 2 = FFMA2 with a constant-bank operand.

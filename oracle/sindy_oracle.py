@@ -208,6 +208,24 @@ def torch_closure(x, dx, Xi, mask, p, sine=False, exp=False, w_sindy_x=1.0, w_si
     return loss.detach(), Xi.grad
 
 
+def torch_adam_loop(x, dx, Xi, mask, p, n_steps, lr, w_sindy_x=1.0, w_sindy_reg=0.0, optimizer="adam", sine=False,
+                    exp=False):
+    """`n_steps` iterations of the Adam loop of train.py:512-530 without sym-reg on one fixed batch
+    (forward, MSELoss, L1 of the unmasked parameters, backward, optimizer.step()) with torch's own optimiser on CPU.
+    Returns (final Xi, [loss at every step before its update], last gradient)."""
+    Xi = torch.nn.Parameter(Xi.detach().clone())
+    opt = torch.optim.Adam([Xi], lr=lr) if optimizer == "adam" else torch.optim.SGD([Xi], lr=lr)
+    losses = []
+    for _ in range(n_steps):
+        pred = torch_theta(x, p, sine, exp) @ (Xi * mask).T
+        loss = w_sindy_x * torch.nn.functional.mse_loss(pred, dx) + w_sindy_reg * torch.norm(Xi, 1)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    return Xi.detach().clone(), losses, Xi.grad.detach().clone()
+
+
 # ---------------------------------------------------------------------------------------------------------
 # linear Lie-derivative regulariser  (train.py:503-507, intended formula `jvp(...)[1]`)
 # ---------------------------------------------------------------------------------------------------------

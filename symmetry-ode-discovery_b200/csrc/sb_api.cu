@@ -279,6 +279,59 @@ int sb_closure_peer(const float* x, const float* dx, int64_t n, const sb_library
   return fused_train_step(x, dx, n, t, xi, mask, flags, packed_out, &co, &pa, ws, ws_bytes, (cudaStream_t)stream);
 }
 
+int sb_fit_step(const float* x, const float* dx, int64_t n, const sb_library* lib, float* xi, const float* mask,
+                const sb_fit_options* opt, float* opt_state, double* packed_out, float* loss_out, float* grad_out,
+                void* ws, int64_t ws_bytes, const void* const* peer_bufs, int world, int rank, uint32_t* epoch_dev,
+                uint32_t call_flags, void* stream) {
+  LibTab t;
+  SB_TRY(build_table(lib, &t));
+  const uint32_t flags = SB_STEP_LOSS | SB_STEP_GRAD;
+  SB_TRY(step_args_ok(x, dx, n, xi, flags, packed_out, ws));
+  SB_TRY(check_ptr(opt, "opt"));
+  if (opt->kind != SB_OPT_SGD && opt->kind != SB_OPT_ADAM) { set_error("unknown optimiser kind %d", opt->kind); return SB_ERR_INVALID; }
+  if (opt->kind == SB_OPT_ADAM) SB_TRY(check_ptr(opt_state, "opt_state"));
+  if (call_flags & ~SB_FIT_W_RESIDENT) { set_error("bad call_flags 0x%x", call_flags); return SB_ERR_INVALID; }
+  const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dx)) & 15u) == 0;
+  if (!aligned || !fused_supported(t, flags)) {
+    set_error("sb_fit_step needs a specialised library and 16-byte aligned inputs"); return SB_ERR_UNSUPPORTED;
+  }
+  PeerArgs pa;
+  if (world > 1) {
+    SB_TRY(check_ptr(peer_bufs, "peer_bufs")); SB_TRY(check_ptr(epoch_dev, "epoch_dev"));
+    if (world > SB_MAX_PEERS || rank < 0 || rank >= world) {
+      set_error("bad world/rank %d/%d (max %d ranks)", world, rank, SB_MAX_PEERS); return SB_ERR_INVALID;
+    }
+    pa.world = world; pa.rank = rank; pa.epoch = epoch_dev;
+    for (int r = 0; r < world; ++r) {
+      if (!peer_bufs[r]) { set_error("peer_bufs[%d] is NULL", r); return SB_ERR_INVALID; }
+      pa.buf[r] = reinterpret_cast<double*>(const_cast<void*>(peer_bufs[r]));
+    }
+  } else if (n == 0) {
+    set_error("sb_fit_step: no samples"); return SB_ERR_INVALID;
+  }
+  ClosureOut co{(double)opt->w_l1, loss_out, grad_out, (double)opt->w_mse};
+  FitArgs fa;
+  fa.kind = opt->kind; fa.lr = opt->lr; fa.beta1 = opt->beta1; fa.beta2 = opt->beta2; fa.eps = opt->eps;
+  fa.xi = xi;
+  if (opt->kind == SB_OPT_ADAM) {
+    const int dk = t.d * t.K;
+    fa.m = opt_state; fa.v = opt_state + dk; fa.step = reinterpret_cast<unsigned int*>(opt_state + 2 * dk);
+  }
+  fa.w_resident = (call_flags & SB_FIT_W_RESIDENT) != 0;
+  return fused_train_step(x, dx, n, t, xi, mask, flags, packed_out, &co, world > 1 ? &pa : nullptr, ws, ws_bytes,
+                          (cudaStream_t)stream, &fa);
+}
+
+int sb_load_w(const sb_library* lib, const float* xi, const float* mask, void* stream) {
+  LibTab t;
+  SB_TRY(build_table(lib, &t));
+  SB_TRY(check_ptr(xi, "xi"));
+  if (!fused_supported(t, SB_STEP_LOSS | SB_STEP_GRAD)) {
+    set_error("sb_load_w: no specialised kernel for this library"); return SB_ERR_UNSUPPORTED;
+  }
+  return fused_load_w(t, xi, mask, (cudaStream_t)stream);
+}
+
 int sb_step_epilogue(const double* packed, const sb_library* lib, const float* xi, const float* mask, double w_l1,
                      float* loss_out, float* grad_out, void* stream) {
   LibTab t;
@@ -328,6 +381,8 @@ int sb_wsindy_integrals(const float* x, int64_t n_traj, int64_t T, const sb_libr
   SB_TRY(check_ptr(x, "x")); SB_TRY(check_ptr(G, "G")); SB_TRY(check_ptr(b, "b"));
   return wsindy_integrals(x, n_traj, T, t, dt, t_max, n_test, G, b, (cudaStream_t)stream);
 }
+
+void sb_debug_trace(void* dev_buf) { fused_set_trace(reinterpret_cast<unsigned long long*>(dev_buf)); }
 
 int sb_fp32_peak(int variant, int iters, double* tflops_host, void* stream) {
   SB_TRY(check_ptr(tflops_host, "tflops_host"));

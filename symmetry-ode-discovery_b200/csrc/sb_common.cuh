@@ -200,6 +200,17 @@ struct ClosureOut {
   double w_l1;
   float* loss;
   float* grad;
+  double w_mse = 1.0;   // weight of the MSE term (w_sindy_x)
+};
+// optimiser update fused into the closure epilogue of the specialised kernel (sb_fit_step)
+struct FitArgs {
+  int kind = SB_OPT_NONE;
+  float lr = 0.f, beta1 = 0.f, beta2 = 0.f, eps = 0.f;
+  float* xi = nullptr;          // parameters, advanced in place
+  float* m = nullptr;           // Adam first / second moments (d×K each)
+  float* v = nullptr;
+  unsigned int* step = nullptr; // Adam step counter (device)
+  bool w_resident = false;      // the constant bank already holds Ξ⊙mask (left there by the previous fit step)
 };
 // loss / gradient from (all-reduced) packed sums; one tiny launch
 int step_epilogue(const double* packed, const LibTab& t, const float* xi, const float* mask, double w_l1,
@@ -224,7 +235,10 @@ bool fused_supported(const LibTab& t, uint32_t flags);
 const char* fused_variant_name(const LibTab& t, uint32_t flags);
 int fused_train_step(const float* x, const float* dx, int64_t n, const LibTab& t, const float* w, const float* mask,
                      uint32_t flags, double* out, const ClosureOut* co, const PeerArgs* peer, void* ws,
-                     int64_t ws_bytes, cudaStream_t s);
+                     int64_t ws_bytes, cudaStream_t s, const FitArgs* fit = nullptr);
+void fused_set_trace(unsigned long long* p);
+// Ξ [⊙ mask] into the constant bank of the specialised kernels (one tiny launch)
+int fused_load_w(const LibTab& t, const float* xi, const float* mask, cudaStream_t s);
 int64_t fused_workspace_bytes(const LibTab& t);
 // specialised per-sample forward and dL/dW (cotangent-weighted feature sums) for the same libraries
 int fused_forward(const float* x, int64_t n, const LibTab& t, const float* w, float* y, cudaStream_t s);

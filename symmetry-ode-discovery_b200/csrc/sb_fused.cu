@@ -27,6 +27,15 @@ namespace {
 
 __constant__ float2 c_w2[kConstW / 2];
 
+unsigned long long* g_trace = nullptr;   // set by sb_debug_trace (timeline of the fused kernel's phases)
+__device__ __forceinline__ void stamp(unsigned long long* trace, int slot) {
+  if (trace && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    trace[(size_t)blockIdx.x * 16 + slot] = t;
+  }
+}
+
 // ---- configuration per library ------------------------------------------------------------------
 // VAR selects a tuning variant (A/B-tested on the B200):
 //   bit 0: 1 = per-stage "empty" mbarriers (no __syncthreads in the tile loop), 0 = CTA barrier per tile
@@ -35,11 +44,14 @@ __constant__ float2 c_w2[kConstW / 2];
 //   bits 3-4: tile ring: 0 = 1024 samples x 4 stages, 1 = 2048 x 3, 2 = 4096 x 2, 3 = 2048 x 4
 //   bit 6: 1 = refill the stage consumed TWO tiles ago (its empty barrier has long completed), 0 = one tile ago
 //   bit 5: 1 = the next sample's x/dx are read from shared memory before the current sample is expanded
+//   bit 7: 1 = equation-by-equation order (pred_i, r_i, acc_i += r_i·Θ for i = 0..d-1) so that the independent
+//          accumulation of equation i can fill the dependent prediction chains of equation i+1
 template <int D, int P, int VAR = 1>
 struct Cfg {
   static constexpr int K = Poly<D, P>::K;
   static constexpr int K2 = (K + 1) / 2;     // packed column pairs
   static constexpr int NV = D * K + 1;       // values reduced per CTA (grad + loss)
+  static constexpr int kRow = (NV + 3) & ~3; // floats per partial row in the workspace (rows stay 16-byte aligned)
   static constexpr int kThreads = 256;
   static constexpr int kWarps = kThreads / 32;
   static constexpr int kTileCode = (VAR >> 3) & 3;        // samples per stage / ring depth
@@ -50,10 +62,11 @@ struct Cfg {
   static constexpr bool kEmptyBarriers = (VAR & 1) != 0;
   static constexpr int kChains = (VAR & 2) ? 2 : 1;
   static constexpr bool kFoldReduce = (VAR & 4) != 0;
+  static constexpr bool kEqOrder = (VAR & 128) != 0;
   // accumulators dominate the register budget: D*K2*2 of them
   static constexpr int kMinBlocks = (D * K2 * 2 + K > 150) ? 1 : ((D * K2 * 2 + K > 40) ? 2 : 3);
   static constexpr size_t kSmemData = (size_t)kStages * 2 * kTile * D * sizeof(float);
-  static constexpr size_t kSmemBytes = kSmemData + 2 * kStages * sizeof(uint64_t) + 16;
+  static constexpr size_t kSmemBytes = kSmemData + (2 * kStages + 1) * sizeof(uint64_t) + 16;
 };
 
 enum { LEFT_RESIDUAL = 0, LEFT_DX = 1 };
@@ -71,7 +84,27 @@ __device__ __forceinline__ void accumulate_sample(const float (&xs)[D], const fl
     m2[kk] = make_float2(m[2 * kk], (2 * kk + 1 < C::K) ? m[2 * kk + 1] : 0.f);
   });
   float r[D];
-  if constexpr (LEFT == LEFT_RESIDUAL) {
+  if constexpr (LEFT == LEFT_RESIDUAL && C::kEqOrder) {
+    constexpr int NC = 4;   // one equation at a time: four partial sums keep its chain short
+    static_for<0, D>([&](auto ic) {
+      constexpr int i = ic;
+      float2 pred[NC];
+      static_for<0, NC>([&](auto c) { pred[c] = make_float2(0.f, 0.f); });
+      static_for<0, C::K2>([&](auto kc) {
+        constexpr int kk = kc;
+        pred[kk % NC] = __ffma2_rn(c_w2[i * C::K2 + kk], m2[kk], pred[kk % NC]);
+      });
+      const float s = ((pred[0].x + pred[0].y) + (pred[1].x + pred[1].y)) + ((pred[2].x + pred[2].y) + (pred[3].x + pred[3].y));
+      r[i] = s - ds[i];
+      lacc = fmaf(r[i], r[i], lacc);
+      const float2 r2 = make_float2(r[i], r[i]);
+      static_for<0, C::K2>([&](auto kc) {
+        constexpr int kk = kc;
+        acc[i][kk] = __ffma2_rn(r2, m2[kk], acc[i][kk]);
+      });
+    });
+    return;
+  } else if constexpr (LEFT == LEFT_RESIDUAL) {
     constexpr int NC = C::kChains;
     float2 pred[D][NC];
     static_for<0, D>([&](auto i) { static_for<0, NC>([&](auto c) { pred[i][c] = make_float2(0.f, 0.f); }); });
@@ -101,13 +134,24 @@ __device__ __forceinline__ void accumulate_sample(const float (&xs)[D], const fl
   });
 }
 
+// b^t by repeated squaring (≤ 32 multiplications; relative error ~1e-15, against `beta ** step` of torch's Adam)
+__device__ __forceinline__ double powi(double b, unsigned int t) {
+  double r = 1.0;
+  while (t) {
+    if (t & 1u) r *= b;
+    b *= b;
+    t >>= 1;
+  }
+  return r;
+}
+
 struct FusedArgs {
   const float* x;
   const float* dx;
   int64_t n;          // samples
   int64_t n_bulk;     // samples covered by TMA tiles (multiple of 4)
   int64_t n_tiles;
-  double* partial;    // [grid][NV]
+  float* partial;     // [grid][kRow]
   unsigned int* ticket;
   double* out;        // packed output base (may be NULL when only the closure epilogue is wanted)
   int64_t out_off;    // offset of this section's d×K block
@@ -117,8 +161,14 @@ struct FusedArgs {
   const float* xi;
   const float* mask;
   double w_l1;
+  double w_mse;       // weight of the MSE term (w_sindy_x; 1 for sb_closure)
   float* loss_out;
   float* grad_out;
+  // optional optimiser update fused into that epilogue (sb_fit_step): Ξ is advanced in place and Ξ⊙mask is packed
+  // into the constant bank for the NEXT launch, so a whole training iteration is this one kernel
+  FitArgs fit;
+  float* w_const;     // device address of the packed constant slot (c_w2)
+  unsigned long long* trace;  // debug: 16 globaltimer stamps per CTA (sb_debug_trace), NULL in production
   // optional in-kernel all-reduce over peer memory (NVLink P2P stores + flags): see the final phase
   PeerArgs peer;
 };
@@ -131,6 +181,7 @@ fused_step_kernel(FusedArgs a) {
   float* tiles = reinterpret_cast<float*>(smem_raw);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + C::kSmemData);
   uint64_t* empty = full + C::kStages;
+  uint64_t* fin_bar = empty + C::kStages;   // completes when the last block's copy of the partial rows has landed
   __shared__ float red[C::kWarps][C::NV];
   __shared__ double fin[C::NV + 2];
   __shared__ int is_last;
@@ -139,30 +190,42 @@ fused_step_kernel(FusedArgs a) {
   const int lane = tid & 31, wid = tid >> 5;
   constexpr int kTileFloats = C::kTile * D;
 
-  auto tile_count = [&](int64_t tile) -> int {
-    const int64_t rem = a.n_bulk - tile * C::kTile;
+  // Every CTA owns one contiguous range of samples, cut in quads (4 samples = 16·d bytes keep the TMA source
+  // 16-byte aligned) so that all CTAs get the same amount of work to within 4 samples — no tile-count quantisation
+  // in the tail, whatever the shard size. The range is consumed in tiles of kTile samples (the last one partial).
+  const int64_t quads = a.n_bulk >> 2;
+  const int64_t s_begin = 4 * (quads * (int64_t)blockIdx.x / (int64_t)gridDim.x);
+  const int64_t s_end = 4 * (quads * ((int64_t)blockIdx.x + 1) / (int64_t)gridDim.x);
+  const int my_tiles = (int)((s_end - s_begin + C::kTile - 1) / C::kTile);
+  auto tile_count = [&](int t) -> int {
+    const int64_t rem = s_end - s_begin - (int64_t)t * C::kTile;
     return (int)(rem < C::kTile ? rem : C::kTile);
   };
-  auto issue = [&](int64_t tile, int stage) {
-    const int cnt = tile_count(tile);
+  auto issue = [&](int t, int stage) {
+    const int cnt = tile_count(t);
     const uint32_t bytes = (uint32_t)cnt * D * sizeof(float);
     float* sx = tiles + (size_t)stage * 2 * kTileFloats;
+    const int64_t off = (s_begin + (int64_t)t * C::kTile) * D;
     mbar_expect_tx(&full[stage], 2 * bytes);
-    tma_load_1d(sx, a.x + tile * (int64_t)kTileFloats, bytes, &full[stage]);
-    tma_load_1d(sx + kTileFloats, a.dx + tile * (int64_t)kTileFloats, bytes, &full[stage]);
+    tma_load_1d(sx, a.x + off, bytes, &full[stage]);
+    tma_load_1d(sx + kTileFloats, a.dx + off, bytes, &full[stage]);
   };
 
+  stamp(a.trace, 0);
+  if (a.trace && tid == 0) {
+    unsigned int smid;
+    asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+    a.trace[(size_t)blockIdx.x * 16 + 7] = smid;
+  }
   if (tid == 0) {
     for (int s = 0; s < C::kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], C::kWarps); }
+    mbar_init(fin_bar, 1);
     fence_mbar_init();
   }
   __syncthreads();
-  if (tid == 0) {
-    for (int s = 0; s < C::kStages; ++s) {
-      const int64_t tile = blockIdx.x + (int64_t)s * gridDim.x;
-      if (tile < a.n_tiles) issue(tile, s);
-    }
-  }
+  // the first tile travels alone (issuing the whole ring at once makes every CTA's first tile queue behind 148 × the
+  // ring in the memory system: first data after 3.5 us instead of ~1 us); the rest of the ring follows once it landed
+  if (tid == 0 && my_tiles > 0) issue(0, 0);
 
   float2 acc[D][C::K2];
   static_for<0, D>([&](auto i) {
@@ -170,15 +233,14 @@ fused_step_kernel(FusedArgs a) {
   });
   float lacc = 0.f;
 
-  int it = 0;
-  for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+  for (int it = 0; it < my_tiles; ++it) {
     const int stage = it % C::kStages;
     const uint32_t parity = (uint32_t)(it / C::kStages) & 1u;
     if constexpr (C::kEmptyBarriers) {
       // refill the stage consumed kLag iterations ago: by now every warp has (almost surely) released it
       if (tid == 0 && it >= C::kLag) {
-        const int64_t next = tile + (int64_t)(C::kStages - C::kLag) * gridDim.x;
-        if (next < a.n_tiles) {
+        const int next = it + C::kStages - C::kLag;
+        if (next < my_tiles) {
           const int ps = (it - C::kLag) % C::kStages;
           mbar_wait(&empty[ps], (uint32_t)((it - C::kLag) / C::kStages) & 1u);
           issue(next, ps);
@@ -186,9 +248,16 @@ fused_step_kernel(FusedArgs a) {
       }
     }
     mbar_wait(&full[stage], parity);
+    if (it == 0) {
+      if (tid == 0) {
+        for (int s = 1; s < C::kStages; ++s)
+          if (s < my_tiles) issue(s, s);
+      }
+      stamp(a.trace, 1);
+    }
     const float* sx = tiles + (size_t)stage * 2 * kTileFloats;
     const float* sd = sx + kTileFloats;
-    const int cnt = tile_count(tile);
+    const int cnt = tile_count(it);
     if constexpr (C::kPrefetch) {
       float xn[D], dn[D];
       if (tid < cnt) static_for<0, D>([&](auto q) { xn[q] = sx[tid * D + q]; dn[q] = sd[tid * D + q]; });
@@ -214,8 +283,8 @@ fused_step_kernel(FusedArgs a) {
     } else {
       __syncthreads();  // every thread is done with this stage before it is refilled
       if (tid == 0) {
-        const int64_t next = tile + (int64_t)C::kStages * gridDim.x;
-        if (next < a.n_tiles) issue(next, stage);
+        const int next = it + C::kStages;
+        if (next < my_tiles) issue(next, stage);
       }
     }
   }
@@ -230,6 +299,7 @@ fused_step_kernel(FusedArgs a) {
     }
   }
 
+  stamp(a.trace, 2);
   // ---- CTA reduction within the warp (fp32), fp64 across warps below ----
   if constexpr (C::kFoldReduce) {
     constexpr int V = ((C::NV + 31) / 32) * 32;
@@ -267,50 +337,112 @@ fused_step_kernel(FusedArgs a) {
     if (lane == 0) red[wid][C::NV - 1] = vl;
   }
   __syncthreads();
-  double* mine = a.partial + (int64_t)blockIdx.x * C::NV;
-  for (int e = tid; e < C::NV; e += C::kThreads) {
+  // per-CTA partial row: the 8 warp sums are added in fp64 and stored as fp32 — the same precision class as the
+  // per-thread fp32 accumulators they come from; everything across CTAs (and ranks) is fp64 again
+  float* mine = a.partial + (int64_t)blockIdx.x * C::kRow;
+  for (int e = tid; e < C::kRow; e += C::kThreads) {
     double v = 0.0;
+    if (e < C::NV) {
 #pragma unroll
-    for (int wq = 0; wq < C::kWarps; ++wq) v += (double)red[wq][e];
-    mine[e] = v;
+      for (int wq = 0; wq < C::kWarps; ++wq) v += (double)red[wq][e];
+    }
+    mine[e] = (float)v;
   }
-  __threadfence();
   __syncthreads();
-  if (tid == 0) is_last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1u);
+  if (tid == 0) {
+    __threadfence();   // cumulative: orders the whole CTA's row (observed through the barrier) before the ticket
+    is_last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1u);
+  }
   __syncthreads();
+  stamp(a.trace, 3);
   if (!is_last) return;
   __threadfence();
 
-  // ---- ordered final reduction over CTAs: warp w adds the partial rows b ≡ w (mod kWarps) with four independent
-  // accumulators (all loads of a lane are in flight together), then the kWarps sub-sums are added in warp order.
-  // The association is fixed by (gridDim, kWarps) only => run-to-run deterministic.
+  // the last block's epilogue inputs travel while it reduces (one element per thread: d·K <= 256 for every shape)
+  static_assert(D * C::K <= C::kThreads, "epilogue assumes one coefficient per thread");
+  float ep_xi = 0.f, ep_mk = 1.f, ep_m = 0.f, ep_v = 0.f;
+  unsigned int ep_step = 0u;
+  const bool ep_on = (a.grad_out || a.loss_out || a.fit.kind != SB_OPT_NONE) && tid < D * C::K;
+  if (ep_on) {
+    ep_xi = __ldcg(a.xi + tid);
+    if (a.mask) ep_mk = __ldcg(a.mask + tid);
+    if (a.fit.kind == SB_OPT_ADAM) { ep_m = __ldcg(a.fit.m + tid); ep_v = __ldcg(a.fit.v + tid); }
+  }
+  if (a.fit.kind == SB_OPT_ADAM) ep_step = __ldcg(a.fit.step);
+
+  // ---- ordered final reduction over CTAs. The partial rows (gridDim × kRow floats, contiguous, in L2) are pulled
+  // into the idle tile ring with TMA bulk copies — no registers, no load/convert serialisation — then warp w adds the
+  // rows b ≡ w (mod kWarps) in row order, a lane owning the column quads {lane, lane+32, ...}, and the kWarps sub-sums
+  // are added in fp64 in warp order. The association is fixed by (gridDim, kWarps) only => run-to-run deterministic.
   {
-    double* sub = reinterpret_cast<double*>(smem_raw);  // the tile ring is idle now: kWarps × NV doubles
-    for (int e0 = 0; e0 < C::NV; e0 += 32) {
-      const int e = e0 + lane;
-      if (e < C::NV) {
-        double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
-        unsigned int b = wid;
-        for (; b + 3 * C::kWarps < gridDim.x; b += 4 * C::kWarps) {
-          v0 += a.partial[(int64_t)b * C::NV + e];
-          v1 += a.partial[(int64_t)(b + C::kWarps) * C::NV + e];
-          v2 += a.partial[(int64_t)(b + 2 * C::kWarps) * C::NV + e];
-          v3 += a.partial[(int64_t)(b + 3 * C::kWarps) * C::NV + e];
-        }
-        for (; b < gridDim.x; b += C::kWarps) v0 += a.partial[(int64_t)b * C::NV + e];
-        sub[wid * C::NV + e] = (v0 + v1) + (v2 + v3);
+    constexpr int kQuads = C::kRow / 4;
+    constexpr int kChunks = (kQuads + 31) / 32;
+    const uint32_t row_bytes = (uint32_t)gridDim.x * C::kRow * (uint32_t)sizeof(float);
+    float* srows = reinterpret_cast<float*>(smem_raw);
+    double* sub = reinterpret_cast<double*>(smem_raw + ((row_bytes + 127u) & ~127u));   // kWarps × kRow doubles
+    if (tid == 0) {
+      // the rows were written through the generic proxy by other SMs and observed via the ticket: order the
+      // async-proxy reads of the bulk copies after them
+      asm volatile("fence.proxy.async;" ::: "memory");
+      mbar_expect_tx(fin_bar, row_bytes);
+      constexpr uint32_t kPiece = 32768;
+      for (uint32_t off = 0; off < row_bytes; off += kPiece) {
+        const uint32_t len = row_bytes - off < kPiece ? row_bytes - off : kPiece;
+        tma_load_1d(smem_raw + off, reinterpret_cast<const unsigned char*>(a.partial) + off, len, fin_bar);
       }
     }
+    mbar_wait(fin_bar, 0);
+    stamp(a.trace, 8);
+    // fp32 -> fp64 conversions and DADDs run at a fraction of the FP32 rate, and so do scalar FP32 instructions next
+    // to the packed ones: the rows are added as unevaluated (hi, lo) fp32 pairs with the error-free TwoSum in packed
+    // f32x2 arithmetic — exact to ~2^-48 like the fp64 sum it replaces — and only the pair totals are converted
+    float2 hi[kChunks][2], lo[kChunks][2];
+    static_for<0, kChunks>([&](auto c) {
+      static_for<0, 2>([&](auto q) { hi[c][q] = make_float2(0.f, 0.f); lo[c][q] = make_float2(0.f, 0.f); });
+    });
+    const float2 neg1 = make_float2(-1.f, -1.f);
+    auto sub2 = [&](float2 u, float2 w) { return __ffma2_rn(w, neg1, u); };   // u - w, one rounding per lane
+    auto two_sum = [&](float2& h, float2& l, float2 x) {
+      const float2 s = __fadd2_rn(h, x);
+      const float2 bb = sub2(s, h);
+      const float2 err = __fadd2_rn(sub2(h, sub2(s, bb)), sub2(x, bb));
+      h = s;
+      l = __fadd2_rn(l, err);
+    };
+    const float4* rows = reinterpret_cast<const float4*>(srows);
+#pragma unroll 2
+    for (unsigned int b = wid; b < gridDim.x; b += C::kWarps) {
+      static_for<0, kChunks>([&](auto cc) {
+        constexpr int c = cc;
+        const int p = c * 32 + lane;
+        if (p < kQuads) {
+          const float4 u = rows[b * kQuads + p];
+          two_sum(hi[c][0], lo[c][0], make_float2(u.x, u.y));
+          two_sum(hi[c][1], lo[c][1], make_float2(u.z, u.w));
+        }
+      });
+    }
+    static_for<0, kChunks>([&](auto cc) {
+      constexpr int c = cc;
+      const int p = c * 32 + lane;
+      if (p < kQuads) {
+        double* o = sub + wid * C::kRow + 4 * p;
+        o[0] = (double)hi[c][0].x + (double)lo[c][0].x; o[1] = (double)hi[c][0].y + (double)lo[c][0].y;
+        o[2] = (double)hi[c][1].x + (double)lo[c][1].x; o[3] = (double)hi[c][1].y + (double)lo[c][1].y;
+      }
+    });
+    stamp(a.trace, 9);
     __syncthreads();
     for (int e = tid; e < C::NV; e += C::kThreads) {
       double v = 0.0;
 #pragma unroll
-      for (int wq = 0; wq < C::kWarps; ++wq) v += sub[wq * C::NV + e];
+      for (int wq = 0; wq < C::kWarps; ++wq) v += sub[wq * C::kRow + e];
       fin[e] = v;
     }
   }
   if (tid == 0) { fin[C::NV] = (double)a.n; *a.ticket = 0u; }
   __syncthreads();
+  stamp(a.trace, 4);
 
   // ---- all-reduce across GPUs inside the kernel (no NCCL launch): each rank's last block pushes its NV+1 totals
   // into slot [parity][rank] of EVERY rank's symmetric buffer with plain peer stores over NVLink, publishes a
@@ -354,6 +486,7 @@ fused_step_kernel(FusedArgs a) {
     __syncthreads();
   }
   const double n_total = fin[C::NV];
+  stamp(a.trace, 5);
 
   if (a.out) {
     for (int e = tid; e < C::NV; e += C::kThreads) {
@@ -367,29 +500,56 @@ fused_step_kernel(FusedArgs a) {
     }
   }
 
-  // ---- closure epilogue (`train.py:663-664,680-683,689`) ----
-  if (a.grad_out || a.loss_out) {
+  // ---- closure epilogue (`train.py:663-664,680-683,689`) [+ optimiser.step() of the Adam loop, `train.py:528-530`] ----
+  if (a.grad_out || a.loss_out || a.fit.kind != SB_OPT_NONE) {
     const double denom = (n_total > 0.0 ? n_total : 1.0) * D;
+    // Adam bias corrections of this step (torch.optim.Adam: step counts from 1)
+    float step_size = a.fit.lr, bc2_sqrt = 1.f;
+    if (a.fit.kind == SB_OPT_ADAM) {
+      const unsigned int t = ep_step + 1u;
+      step_size = (float)((double)a.fit.lr / (1.0 - powi((double)a.fit.beta1, t)));
+      bc2_sqrt = (float)sqrt(1.0 - powi((double)a.fit.beta2, t));
+    }
     double l1 = 0.0;
-    for (int e = tid; e < D * C::K; e += C::kThreads) {
-      const float xi = a.xi[e];
-      const float mk = a.mask ? a.mask[e] : 1.f;
-      l1 += fabs((double)xi);
-      if (a.grad_out) {
-        const double sgn = (xi > 0.f) ? 1.0 : ((xi < 0.f) ? -1.0 : 0.0);
-        a.grad_out[e] = (float)(fin[e] * (2.0 / denom) * (double)mk + a.w_l1 * sgn);
+    if (ep_on) {
+      const int e = tid;
+      const float xi = ep_xi, mk = ep_mk;
+      l1 = fabs((double)xi);
+      const double sgn = (xi > 0.f) ? 1.0 : ((xi < 0.f) ? -1.0 : 0.0);
+      const float g = (float)(fin[e] * (2.0 / denom) * a.w_mse * (double)mk + a.w_l1 * sgn);
+      if (a.grad_out) a.grad_out[e] = g;
+      if (a.fit.kind != SB_OPT_NONE) {
+        float xn;
+        if (a.fit.kind == SB_OPT_ADAM) {
+          // the arithmetic of torch's Adam in fp32: lerp, mul+addcmul, sqrt / sqrt(bc2) + eps, addcdiv
+          const float m = fmaf(1.f - a.fit.beta1, g - ep_m, ep_m);
+          const float v = fmaf((1.f - a.fit.beta2) * g, g, ep_v * a.fit.beta2);
+          a.fit.m[e] = m;
+          a.fit.v[e] = v;
+          const float den = __fdiv_rn(__fsqrt_rn(v), bc2_sqrt) + a.fit.eps;
+          xn = xi - step_size * __fdiv_rn(m, den);
+        } else {
+          xn = xi - a.fit.lr * g;
+        }
+        a.fit.xi[e] = xn;
+        const int i = e / C::K, k = e % C::K;
+        a.w_const[i * 2 * C::K2 + k] = xn * mk;   // W of the next launch (odd-K padding stays zero)
       }
     }
     l1 = warp_sum(l1);
     __shared__ double l1w[C::kWarps];
     if (lane == 0) l1w[wid] = l1;
     __syncthreads();
-    if (tid == 0 && a.loss_out) {
-      double t = 0.0;
-      for (int wq = 0; wq < C::kWarps; ++wq) t += l1w[wq];
-      *a.loss_out = (float)(fin[C::NV - 1] / denom + a.w_l1 * t);
+    if (tid == 0) {
+      if (a.loss_out) {
+        double t = 0.0;
+        for (int wq = 0; wq < C::kWarps; ++wq) t += l1w[wq];
+        *a.loss_out = (float)(a.w_mse * fin[C::NV - 1] / denom + a.w_l1 * t);
+      }
+      if (a.fit.kind == SB_OPT_ADAM) *a.fit.step = ep_step + 1u;
     }
   }
+  stamp(a.trace, 6);
 }
 
 // Ξ (d×K fp32) [⊙ mask] -> the packed constant slot of the fused kernels (pairs, zero padded for odd K)
@@ -411,10 +571,13 @@ int tuning_variant() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("SB_FUSED_VARIANT");
-    // A/B on B200 (closure at n = 1.94e7, graph replay): 3: 287.1 us, 7: 286.9, 11: 273.4, 19: 271.5 (worse tail at
-    // small n), 27: 279.2, 75: 273.2, 91: 281.1; at N = 1e8: 0: 1.450 ms, 1: 1.397, 2: 1.453, 3: 1.384
-    v = e ? atoi(e) : 11;
-    if (v < 0 || v > 127) v = 11;
+    // A/B on B200 at N = 1e8 (one launch, median of 15): 15: 1.335 ms, 11: 1.365, 47: 1.387, 143: 1.378; at the 8-GPU
+    // shard size (1.25e7 samples, whole fit step): 15: 174.9 us, 11: 180.3, 23: 177.7, 19: 183.6. Earlier rounds of the
+    // same A/B (CTA barrier per tile, one prediction chain, 1024x4 ring, unroll by 2: spills) were slower and are gone,
+    // and so is a packed-monomial schedule (23 mul.f32x2 + 6 FMUL instead of 52 FMUL, same bits): 1.367 ms against
+    // 1.342 — a scalar FMUL holds the FMA pipe one cycle, a packed one two, so packing only saves issue slots.
+    v = e ? atoi(e) : 15;
+    if (v < 0 || v > 511) v = 15;
   }
   return v;
 }
@@ -439,15 +602,21 @@ int launch_fused_var(FusedArgs a, void* ws, int64_t ws_bytes, cudaStream_t s) {
   }
   a.n_bulk = a.n & ~(int64_t)3;
   a.n_tiles = (a.n_bulk + C::kTile - 1) / C::kTile;
-  int64_t grid = a.n_tiles < grid_cached[dev] ? a.n_tiles : grid_cached[dev];
+  // one contiguous, equally sized range per CTA; no more CTAs than half-tiles of work
+  int64_t grid = (a.n_bulk + C::kTile / 2 - 1) / (C::kTile / 2);
+  if (grid > grid_cached[dev]) grid = grid_cached[dev];
+  // the last block stages all partial rows (+ kWarps sub-sum rows of doubles) in the tile ring
+  constexpr int64_t kRowsFit = ((int64_t)C::kSmemData - 128 - (int64_t)C::kWarps * C::kRow * 8) / (C::kRow * 4);
+  if (grid > kRowsFit) grid = kRowsFit;
   if (grid < 1) grid = 1;
-  const int64_t need = kWsHeaderBytes + grid * C::NV * (int64_t)sizeof(double);
+  const int64_t need = kWsHeaderBytes + grid * C::kRow * (int64_t)sizeof(float);
   if (ws_bytes < need) {
     set_error("workspace too small: %lld < %lld bytes", (long long)ws_bytes, (long long)need);
     return SB_ERR_WORKSPACE;
   }
   a.ticket = reinterpret_cast<unsigned int*>(ws);
-  a.partial = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + kWsHeaderBytes);
+  a.partial = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + kWsHeaderBytes);
+  a.trace = g_trace;
   kern<<<(unsigned)grid, C::kThreads, C::kSmemBytes, s>>>(a);
   SB_LAUNCH_CHECK("fused_step_kernel");
   return SB_OK;
@@ -457,22 +626,19 @@ template <int D, int P, int LEFT>
 int launch_fused(const FusedArgs& a, void* ws, int64_t ws_bytes, cudaStream_t s) {
   if constexpr (D == 3 && P == 5) {  // the headline shape carries the A/B variants
     switch (tuning_variant()) {
-      case 0: return launch_fused_var<D, P, LEFT, 0>(a, ws, ws_bytes, s);
-      case 1: return launch_fused_var<D, P, LEFT, 1>(a, ws, ws_bytes, s);
-      case 2: return launch_fused_var<D, P, LEFT, 2>(a, ws, ws_bytes, s);
-      case 3: return launch_fused_var<D, P, LEFT, 3>(a, ws, ws_bytes, s);
-      case 7: return launch_fused_var<D, P, LEFT, 7>(a, ws, ws_bytes, s);
+      case 11: return launch_fused_var<D, P, LEFT, 11>(a, ws, ws_bytes, s);
       case 19: return launch_fused_var<D, P, LEFT, 19>(a, ws, ws_bytes, s);
-      default: return launch_fused_var<D, P, LEFT, 11>(a, ws, ws_bytes, s);
+      case 23: return launch_fused_var<D, P, LEFT, 23>(a, ws, ws_bytes, s);
+      case 47: return launch_fused_var<D, P, LEFT, 47>(a, ws, ws_bytes, s);
+      case 143: return launch_fused_var<D, P, LEFT, 143>(a, ws, ws_bytes, s);
+      default: return launch_fused_var<D, P, LEFT, 15>(a, ws, ws_bytes, s);
     }
   }
   return launch_fused_var<D, P, LEFT, 5>(a, ws, ws_bytes, s);  // small libraries: empty-barrier ring + folded reduction
 }
 
-// Ξ [⊙ mask] -> constant slot, one tiny launch on the stream (replaces a D2D cudaMemcpyToSymbolAsync + a mul)
-template <int D, int P>
-int upload_w(const float* xi, const float* mask, cudaStream_t s) {
-  using C = Cfg<D, P>;
+// device address of the packed constant slot on the current device
+int const_slot(float** out) {
   static float* base[64] = {nullptr};
   int dev = 0;
   SB_CUDA_TRY(cudaGetDevice(&dev));
@@ -482,28 +648,48 @@ int upload_w(const float* xi, const float* mask, cudaStream_t s) {
     SB_CUDA_TRY(cudaGetSymbolAddress(&p, c_w2));
     base[dev] = reinterpret_cast<float*>(p);
   }
+  *out = base[dev];
+  return SB_OK;
+}
+
+// Ξ [⊙ mask] -> constant slot, one tiny launch on the stream (replaces a D2D cudaMemcpyToSymbolAsync + a mul)
+template <int D, int P>
+int upload_w(const float* xi, const float* mask, cudaStream_t s) {
+  using C = Cfg<D, P>;
+  float* base = nullptr;
+  int st = const_slot(&base);
+  if (st != SB_OK) return st;
   const int total = D * C::K2 * 2;
-  pack_w_kernel<<<(total + 255) / 256, 256, 0, s>>>(xi, mask, base[dev], D, C::K, C::K2);
+  pack_w_kernel<<<(total + 255) / 256, 256, 0, s>>>(xi, mask, base, D, C::K, C::K2);
   SB_LAUNCH_CHECK("pack_w_kernel");
   return SB_OK;
 }
 
 template <int D, int P>
 int run_fused(const float* x, const float* dx, int64_t n, const float* w, const float* mask, uint32_t flags,
-              double* out, const ClosureOut* co, const PeerArgs* peer, void* ws, int64_t ws_bytes, cudaStream_t s) {
+              double* out, const ClosureOut* co, const PeerArgs* peer, void* ws, int64_t ws_bytes, cudaStream_t s,
+              const FitArgs* fit) {
   using C = Cfg<D, P>;
   FusedArgs a{};
-  a.x = x; a.dx = dx; a.n = n; a.out = out;
+  a.x = x; a.dx = dx; a.n = n; a.out = out; a.w_mse = 1.0;
   const bool resid = flags & (SB_STEP_LOSS | SB_STEP_GRAD);
   if (resid) {
-    int st = upload_w<D, P>(w, mask, s);
+    int st = SB_OK;
+    if (!(fit && fit->w_resident)) st = upload_w<D, P>(w, mask, s);
     if (st != SB_OK) return st;
     a.out_off = 2; a.out_transposed = 0; a.write_header = 1;
-    if (co) { a.xi = w; a.mask = mask; a.w_l1 = co->w_l1; a.loss_out = co->loss; a.grad_out = co->grad; }
+    if (co) {
+      a.xi = w; a.mask = mask; a.w_l1 = co->w_l1; a.w_mse = co->w_mse; a.loss_out = co->loss; a.grad_out = co->grad;
+    }
+    if (fit && fit->kind != SB_OPT_NONE) {
+      a.fit = *fit;
+      st = const_slot(&a.w_const);
+      if (st != SB_OK) return st;
+    }
     if (peer) a.peer = *peer;
     st = launch_fused<D, P, LEFT_RESIDUAL>(a, ws, ws_bytes, s);
     if (st != SB_OK) return st;
-    a.loss_out = nullptr; a.grad_out = nullptr; a.peer = PeerArgs{};
+    a.loss_out = nullptr; a.grad_out = nullptr; a.peer = PeerArgs{}; a.fit = FitArgs{};
   }
   if (flags & SB_STEP_B) {
     // the ΘᵀẊ section follows the (optional) gradient and Gram sections of the packed layout
@@ -568,6 +754,8 @@ int run_weighted_sums(const float* x, const float* g, int64_t n, double* out, vo
 
 }  // namespace
 
+void fused_set_trace(unsigned long long* p) { g_trace = p; }
+
 bool fused_supported(const LibTab& t, uint32_t flags) {
   if (t.sine || t.exp_) return false;
   if (flags & SB_STEP_GRAM) return false;
@@ -606,15 +794,23 @@ int fused_weighted_sums(const float* x, const float* g, int64_t n, const LibTab&
 }
 
 int64_t fused_workspace_bytes(const LibTab& t) {
-  return kWsHeaderBytes + (int64_t)kMaxPartialBlocks * ((int64_t)t.d * t.K + 1) * (int64_t)sizeof(double);
+  return kWsHeaderBytes + (int64_t)kMaxPartialBlocks * ((int64_t)t.d * t.K + 4) * (int64_t)sizeof(float);
+}
+
+int fused_load_w(const LibTab& t, const float* xi, const float* mask, cudaStream_t s) {
+#define X(D, P) if (t.d == D && t.n_poly == n_poly_terms(D, P)) return upload_w<D, P>(xi, mask, s);
+  SB_FUSED_SHAPES(X)
+#undef X
+  set_error("no fused kernel for d=%d K=%d", t.d, t.K);
+  return SB_ERR_UNSUPPORTED;
 }
 
 int fused_train_step(const float* x, const float* dx, int64_t n, const LibTab& t, const float* w, const float* mask,
                      uint32_t flags, double* out, const ClosureOut* co, const PeerArgs* peer, void* ws,
-                     int64_t ws_bytes, cudaStream_t s) {
+                     int64_t ws_bytes, cudaStream_t s, const FitArgs* fit) {
 #define X(D, P)                                                  \
   if (t.d == D && t.n_poly == n_poly_terms(D, P))                \
-    return run_fused<D, P>(x, dx, n, w, mask, flags, out, co, peer, ws, ws_bytes, s);
+    return run_fused<D, P>(x, dx, n, w, mask, flags, out, co, peer, ws, ws_bytes, s, fit);
   SB_FUSED_SHAPES(X)
 #undef X
   set_error("no fused kernel for d=%d K=%d", t.d, t.K);

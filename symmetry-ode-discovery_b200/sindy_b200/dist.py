@@ -213,6 +213,82 @@ class ShardedTrainStep:
         return self._static_res
 
 
+class FitStepper:
+    """A whole training iteration (closure + optimiser update, `train.py:512-530` without sym-reg) as ONE kernel
+    launch per rank, replayed as a CUDA graph: the fused kernel's last block all-reduces the sums over NVLink peer
+    memory (several ranks), evaluates loss and gradient, applies Adam/SGD to Ξ in place and packs Ξ⊙mask into the
+    constant bank for the next launch (sb_fit_step). Ξ, mask and the optimiser state are replicated: every rank
+    applies the identical update. Needs a specialised library; raises otherwise (no fallback).
+
+    step() -> loss tensor (static buffer; the value at the parameters BEFORE the update). `xi`, `grad` are the
+    static parameter / gradient tensors. Call load(xi, mask) after changing parameters or mask from outside
+    (thresholding): it also resets nothing else — the Adam state is kept, like torch's optimiser does.
+    """
+
+    def __init__(self, lib: Library, x: torch.Tensor, dx: torch.Tensor, kind: str = "adam", lr: float = 1e-3,
+                 betas=(0.9, 0.999), eps: float = 1e-8, w_mse: float = 1.0, w_l1: float = 0.0, group=None,
+                 use_graph: bool = True, use_peer: bool = True):
+        self.lib, self.x, self.dx = lib, x, dx
+        self.kind, self.lr, self.betas, self.eps, self.w_mse, self.w_l1 = kind, lr, betas, eps, w_mse, w_l1
+        dev = x.device
+        d, K = lib.dim, lib.K
+        self.xi = torch.zeros(d, K, dtype=torch.float32, device=dev)
+        self.mask = torch.ones(d, K, dtype=torch.float32, device=dev)
+        self.state = native.fit_state(lib, dev)
+        self.packed = torch.empty(2 + d * K, dtype=torch.float64, device=dev)
+        self.loss = torch.empty((), dtype=torch.float32, device=dev)
+        self.grad = torch.empty(d, K, dtype=torch.float32, device=dev)
+        self.peer = None
+        if _world(group) > 1:
+            self.peer = PeerExchange.create(lib, dev, group) if use_peer else None
+            if self.peer is None:
+                raise RuntimeError("FitStepper over several ranks needs the peer exchange (symmetric memory); use "
+                                   "ShardedTrainStep for the NCCL path")
+        self._use_graph = use_graph
+        self._graph = None
+        self._loaded = False
+
+    def load(self, xi: torch.Tensor, mask: Optional[torch.Tensor] = None, reset_state: bool = False):
+        self.xi.copy_(xi)
+        if mask is not None:
+            self.mask.copy_(mask)
+        if reset_state:
+            self.state.zero_()
+        native.load_w(self.xi, self.mask, self.lib)
+        self._loaded = True
+
+    def _launch(self):
+        p = self.peer
+        native.fit_step(self.x, self.dx, self.xi, self.mask, self.lib, self.kind, self.lr, self.betas, self.eps,
+                        self.w_mse, self.w_l1, state=self.state, w_resident=True, packed=self.packed, loss=self.loss,
+                        grad=self.grad, peer_ptrs=p.ptrs if p else None, rank=p.rank if p else 0,
+                        epoch=p.epoch if p else None)
+
+    def step(self):
+        if not self._loaded:
+            raise ValueError("call load(xi, mask) first")
+        if not self._use_graph:
+            self._launch()
+            return self.loss
+        if self._graph is None:
+            # capture only: nothing inside the graph has run yet, so parameters, Adam state and the peer epoch are
+            # exactly what load() left (the workspace and the occupancy query are warmed by load_w / earlier calls)
+            keep_xi, keep_state = self.xi.clone(), self.state.clone()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._launch()   # warm-up outside capture (first-call attribute/occupancy queries)
+            torch.cuda.current_stream().wait_stream(side)
+            self.xi.copy_(keep_xi)
+            self.state.copy_(keep_state)
+            native.load_w(self.xi, self.mask, self.lib)
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self._launch()
+        self._graph.replay()
+        return self.loss
+
+
 class HostStreamedStep:
     """Fused train step over (x, dx) that live in PINNED HOST memory: chunks are copied host->device on two
     alternating streams into two staging buffers and reduced by the kernel as they land; the packed sums of the

@@ -23,10 +23,17 @@ SB_STEP_LOSS, SB_STEP_GRAD, SB_STEP_GRAM, SB_STEP_B = 1, 2, 4, 8
 SB_F32, SB_F64 = 0, 1
 SB_EULER, SB_RK4 = 0, 1
 SB_MAX_DIM, SB_MAX_POLY, SB_MAX_TERMS = 8, 5, 256
+SB_OPT_NONE, SB_OPT_SGD, SB_OPT_ADAM = 0, 1, 2
+SB_FIT_W_RESIDENT = 1
 
 
 class _CLibrary(ctypes.Structure):
     _fields_ = [("dim", c_int32), ("poly_order", c_int32), ("include_sine", c_int32), ("include_exp", c_int32)]
+
+
+class _CFitOptions(ctypes.Structure):
+    _fields_ = [("kind", c_int32), ("lr", c_float), ("beta1", c_float), ("beta2", c_float), ("eps", c_float),
+                ("w_mse", c_float), ("w_l1", c_float)]
 
 
 # every symbol include/sindy_b200.h declares: name -> (restype, argtypes)
@@ -54,6 +61,10 @@ _SIGNATURES = {
                                 c_void_p, c_void_p, c_void_p, c_int64, POINTER(c_void_p), c_int, c_int, c_void_p,
                                 c_void_p]),
     "sb_peer_buffer_bytes": (c_int64, [POINTER(_CLibrary), c_int]),
+    "sb_fit_step": (c_int, [c_void_p, c_void_p, c_int64, POINTER(_CLibrary), c_void_p, c_void_p,
+                            POINTER(_CFitOptions), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                            POINTER(c_void_p), c_int, c_int, c_void_p, c_uint32, c_void_p]),
+    "sb_load_w": (c_int, [POINTER(_CLibrary), c_void_p, c_void_p, c_void_p]),
     "sb_step_epilogue": (c_int, [c_void_p, POINTER(_CLibrary), c_void_p, c_void_p, c_double, c_void_p, c_void_p,
                                  c_void_p]),
     "sb_train_step_variant": (c_char_p, [POINTER(_CLibrary), c_uint32]),
@@ -61,6 +72,7 @@ _SIGNATURES = {
                            c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sb_wsindy_integrals": (c_int, [c_void_p, c_int64, c_int64, POINTER(_CLibrary), c_float, c_double, c_int,
                                     c_void_p, c_void_p, c_void_p]),
+    "sb_debug_trace": (None, [c_void_p]),
     "sb_fp32_peak": (c_int, [c_int, c_int, POINTER(c_double), c_void_p]),
 }
 
@@ -336,6 +348,59 @@ def closure_peer(x: torch.Tensor, dx: torch.Tensor, xi: torch.Tensor, mask: Opti
                                       _ptr(mk), float(w_l1), packed.data_ptr(), loss.data_ptr(), grad.data_ptr(),
                                       ws.data_ptr(), ws.numel(), arr, world, int(rank), epoch.data_ptr(),
                                       _stream(dev)), "sb_closure_peer")
+    return loss, grad, packed
+
+
+def fit_state(lib: Library, device) -> torch.Tensor:
+    """Zeroed Adam state of sb_fit_step: [m (d×K) | v (d×K) | step counter] as 2·d·K+1 32-bit words."""
+    return torch.zeros(2 * lib.dim * lib.K + 1, dtype=torch.float32, device=device)
+
+
+def load_w(xi: torch.Tensor, mask: Optional[torch.Tensor], lib: Library) -> None:
+    """Ξ⊙mask into the constant bank of the specialised kernels (makes SB_FIT_W_RESIDENT true)."""
+    xi = _f32c(xi, "xi")
+    mk = _f32c(mask, "mask") if mask is not None else None
+    with torch.cuda.device(xi.device):
+        _check(load().sb_load_w(ctypes.byref(lib.c()), xi.data_ptr(), _ptr(mk), _stream(xi.device)), "sb_load_w")
+
+
+def fit_step(x: torch.Tensor, dx: torch.Tensor, xi: torch.Tensor, mask: Optional[torch.Tensor], lib: Library,
+             kind: str = "adam", lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, w_mse: float = 1.0,
+             w_l1: float = 0.0, state: Optional[torch.Tensor] = None, w_resident: bool = False,
+             packed: Optional[torch.Tensor] = None, loss: Optional[torch.Tensor] = None,
+             grad: Optional[torch.Tensor] = None, peer_ptrs=None, rank: int = 0,
+             epoch: Optional[torch.Tensor] = None):
+    """One iteration of the Adam (or SGD) loop `train.py:512-530` in ONE launch: loss and dL/dΞ at the current
+    parameters, then `xi` (fp32 CUDA, contiguous) is advanced IN PLACE. Returns (loss, grad, packed). `state`
+    = fit_state(lib) for Adam. With peer_ptrs the samples are sharded over the ranks (see closure_peer)."""
+    xf = _flat(_f32c(x, "x"), lib.dim, "x")
+    dxf = _flat(_f32c(dx, "dx"), lib.dim, "dx")
+    _require_cuda(xi, "xi")
+    if xi.dtype != torch.float32 or not xi.is_contiguous():
+        raise ValueError("`xi` is updated in place: it must be a contiguous float32 CUDA tensor")
+    mk = _f32c(mask, "mask") if mask is not None else None
+    kinds = {"sgd": SB_OPT_SGD, "adam": SB_OPT_ADAM}
+    if kind not in kinds:
+        raise ValueError(f"unknown optimiser {kind!r}")
+    if kind == "adam" and (state is None or state.numel() < 2 * lib.dim * lib.K + 1 or not state.is_cuda):
+        raise ValueError("Adam needs `state` = fit_state(lib, device)")
+    dev = xf.device
+    d, K = lib.dim, lib.K
+    if packed is None:
+        packed = torch.empty(2 + d * K, dtype=torch.float64, device=dev)
+    if loss is None:
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+    if grad is None:
+        grad = torch.empty(d, K, dtype=torch.float32, device=dev)
+    opt = _CFitOptions(kinds[kind], float(lr), float(betas[0]), float(betas[1]), float(eps), float(w_mse), float(w_l1))
+    world = len(peer_ptrs) if peer_ptrs else 1
+    arr = (c_void_p * world)(*[int(p) for p in peer_ptrs]) if world > 1 else None
+    ws = _workspace(lib, dev)
+    with torch.cuda.device(dev):
+        _check(load().sb_fit_step(xf.data_ptr(), dxf.data_ptr(), xf.shape[0], ctypes.byref(lib.c()), xi.data_ptr(),
+                                  _ptr(mk), ctypes.byref(opt), _ptr(state), packed.data_ptr(), loss.data_ptr(),
+                                  grad.data_ptr(), ws.data_ptr(), ws.numel(), arr, world, int(rank), _ptr(epoch),
+                                  SB_FIT_W_RESIDENT if w_resident else 0, _stream(dev)), "sb_fit_step")
     return loss, grad, packed
 
 

@@ -21,6 +21,16 @@ def pytest_configure(config):
         subprocess.run(["make", "-j8", "-C", os.path.join(PKG, "csrc")], check=True, stdout=subprocess.DEVNULL)
 
 
+def pytest_report_header(config):
+    """GPU identity in the test header, so that a numerical outlier can be tied to a physical device."""
+    try:
+        out = subprocess.run(["nvidia-smi", "--query-gpu=name,serial,uuid", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip()
+        return [f"gpu: {line}" for line in out.splitlines()] if out else None
+    except (OSError, subprocess.SubprocessError):
+        return None
+
+
 class Golden:
     def __init__(self, name):
         self._z = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))

@@ -483,11 +483,11 @@ def test_fused_variants_agree(nat):
         "print(json.dumps(out.cpu().tolist()))\n"
     ) % (os.path.join(os.path.dirname(__file__), ".."), os.path.join(os.path.dirname(__file__), "..", "symmetry-ode-discovery_b200"))
     res = []
-    for v in ("0", "1", "2", "3", "7", "11", "19"):
+    for v in ("15", "47", "11", "19", "23", "143"):
         env = dict(os.environ, SB_FUSED_VARIANT=v)
         out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True).stdout
         res.append(np.array(json.loads(out.strip().splitlines()[-1])))
     for r in res[1:]:
         assert np.abs(r - res[0]).max() / np.abs(res[0]).max() < 1e-6
-    assert np.array_equal(res[0], res[1])      # variants 0 and 1 differ only in synchronisation: identical bits
-    assert np.array_equal(res[2], res[3])
+    assert np.array_equal(res[0], res[1])      # 15 and 47 differ only in when a sample is read from smem: identical bits
+

@@ -68,3 +68,80 @@ def test_cached_gram_lbfgs_matches_fused_closure_fit(golden):
     la = reg.mse_loss(x, dx); la.backward(); ga = reg.Xi.grad.clone(); reg.zero_grad()
     lb = reg.mse_loss_from_statistics(stats); lb.backward()
     assert abs(float(la) - float(lb)) < 1e-5 * abs(float(la)) and rel(reg.Xi.grad, ga) < 1e-4
+
+
+@pytest.mark.parametrize("d,p", [(3, 5), (2, 2), (2, 3), (3, 3)])
+@pytest.mark.parametrize("kind", ["adam", "sgd"])
+def test_fit_step_one_launch_iteration_vs_torch_optimizer(d, p, kind):
+    """sb_fit_step (closure + optimiser.step() + next W in ONE launch) against the oracle loop with torch's own
+    Adam / SGD on CPU (`train.py:512-530`): losses at every step, final parameters, masked entries included."""
+    from oracle import sindy_oracle as O
+    from sindy_b200 import native
+    rng = np.random.default_rng(d * 10 + p)
+    lib = native.Library(d, p)
+    K = lib.K
+    n = 30_001
+    x = rng.uniform(-1, 1, (n, d)).astype(np.float32)
+    Xi_true = (rng.standard_normal((d, K)) * (rng.random((d, K)) > 0.6)).astype(np.float32)
+    dx = (O.theta(x, p) @ Xi_true.T + 0.01 * rng.standard_normal((n, d))).astype(np.float32)
+    Xi0 = (0.3 * rng.standard_normal((d, K))).astype(np.float32)
+    mask = (rng.random((d, K)) > 0.2).astype(np.float32)
+    steps, lr, w_x, w_l1 = 25, (0.02 if kind == "adam" else 0.05), 0.7, 1e-3
+    Xi_ref, losses_ref, grad_ref = O.torch_adam_loop(torch.from_numpy(x), torch.from_numpy(dx), torch.from_numpy(Xi0),
+                                                     torch.from_numpy(mask), p, steps, lr, w_x, w_l1, kind)
+    xd, dxd, mk = dev(x), dev(dx), dev(mask)
+    xi = dev(Xi0).contiguous()
+    state = native.fit_state(lib, xi.device)
+    losses = []
+    for it in range(steps):
+        # first call packs W itself; afterwards the previous launch has left W in the constant bank
+        loss, grad, packed = native.fit_step(xd, dxd, xi, mk, lib, kind, lr, w_mse=w_x, w_l1=w_l1, state=state,
+                                             w_resident=(it > 0))
+        losses.append(float(loss))
+    assert float(packed[1]) == n
+    np.testing.assert_allclose(losses, losses_ref, rtol=2e-5)
+    assert rel(grad, grad_ref) < 2e-4
+    assert rel(xi, Xi_ref) < 2e-5, rel(xi, Xi_ref)
+    if kind == "adam":
+        assert int(state[-1:].view(torch.int32)) == steps
+    # the parameters the NEXT launch would use are the updated ones: a plain closure at xi gives the same loss
+    l_chk, _, _ = native.closure(xd, dxd, xi, mk, lib, w_l1)
+    l_next, _, _ = native.fit_step(xd, dxd, xi.clone(), mk, lib, kind, lr, w_mse=1.0, w_l1=w_l1,
+                                   state=native.fit_state(lib, xi.device), w_resident=False)
+    assert abs(float(l_chk) - float(l_next)) <= 1e-6 * abs(float(l_chk))
+
+
+def test_fit_stepper_graph_replay_matches_eager():
+    """FitStepper (CUDA-graph replay of the one-launch iteration, W resident in the constant bank across replays,
+    reload after an external mask change) reproduces the eager sb_closure + torch.optim.Adam sequence."""
+    from sindy_b200 import native
+    from sindy_b200.dist import FitStepper
+    lib = native.Library(3, 5)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    n = 200_000
+    x = torch.rand(n, 3, device="cuda", generator=g) * 2 - 1
+    dx = torch.randn(n, 3, device="cuda", generator=g)
+    Xi0 = 0.1 * torch.randn(3, 56, device="cuda", generator=g)
+    mask = torch.ones(3, 56, device="cuda")
+    # eager reference first (sb_closure repacks the constant bank, so it must not run between the stepper's launches)
+    ref = torch.nn.Parameter(Xi0.clone())
+    opt = torch.optim.Adam([ref], lr=1e-2)
+    ref_losses, ref_params, masks = [], [], []
+    for it in range(12):
+        if it == 6:   # thresholding from outside: new mask, parameters kept, optimiser state kept
+            mask = (ref.detach().abs() > 0.05).float()
+        masks.append(mask.clone())
+        l_ref, g_ref, _ = native.closure(x, dx, ref.detach(), mask, lib, 1e-3)
+        ref_losses.append(float(l_ref))
+        ref.grad = g_ref.clone()
+        opt.step()
+        ref_params.append(ref.detach().clone())
+    st = FitStepper(lib, x, dx, "adam", lr=1e-2, w_l1=1e-3)
+    st.load(Xi0, masks[0])
+    for it in range(12):
+        if it == 6:
+            st.load(st.xi.clone(), masks[6])
+        loss = st.step()
+        assert abs(float(loss) - ref_losses[it]) <= 2e-5 * abs(ref_losses[it]), it
+        assert rel(st.xi, ref_params[it]) < 2e-5, (it, rel(st.xi, ref_params[it]))
+    assert int(st.state[-1:].view(torch.int32)) == 12

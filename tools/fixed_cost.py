@@ -12,9 +12,16 @@ dx = torch.randn(nmax, 3, device="cuda", generator=g)
 W = torch.randn(3, 56, device="cuda", generator=g)
 mask = torch.ones_like(W)
 pk = torch.empty(170, dtype=torch.float64, device="cuda"); ls = torch.empty((), device="cuda"); gr = torch.empty(3, 56, device="cuda")
+state = native.fit_state(lib, "cuda")
+xi = W.clone()
+mode = sys.argv[1] if len(sys.argv) > 1 else "closure"
 for t in (1, 82, 128):
     n = 148 * 1024 * t
-    f = lambda: native.closure(x[:n], dx[:n], W, mask, lib, 0.0, packed=pk, loss=ls, grad=gr)
+    if mode == "fit":   # one launch per iteration: closure + Adam + next W
+        native.load_w(xi, mask, lib)
+        f = lambda: native.fit_step(x[:n], dx[:n], xi, mask, lib, "adam", 1e-4, state=state, w_resident=True, packed=pk, loss=ls, grad=gr)
+    else:
+        f = lambda: native.closure(x[:n], dx[:n], W, mask, lib, 0.0, packed=pk, loss=ls, grad=gr)
     for _ in range(3): f()
     torch.cuda.synchronize()
     gph = torch.cuda.CUDAGraph()
@@ -29,4 +36,4 @@ for t in (1, 82, 128):
     for _ in range(5): gph.replay()
     b.record(); torch.cuda.synchronize()
     us = 1e3 * a.elapsed_time(b) / 100
-    print(f"tiles/CTA {t:4d} n={n:10d}: {us:8.2f} us per closure (graph of 20, back to back)  per-tile {us/t:6.3f} us")
+    print(f"tiles/CTA {t:4d} n={n:10d}: {us:8.2f} us per {mode} (graph of 20, back to back)  per-tile {us/t:6.3f} us")

@@ -6,7 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "symmetry-ode-discovery_b200")]
 import numpy as np, torch, torch.distributed as dist
 from sindy_b200 import native
-from sindy_b200.dist import ShardedTrainStep
+from sindy_b200.dist import FitStepper, ShardedTrainStep
 
 rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(lr)
@@ -43,10 +43,26 @@ for (d, p) in ((3, 5), (2, 3)):
     for _ in range(4):
         l_g, g_g = gstep.step(Xit, mt, 0.01)
     gr = float(l_g) == l_p and torch.equal(g_g, g_p)
-    good = e1 < 1e-6 and e2 < 1e-6 and e3 < 1e-5 and e4 < 1e-5 and same and rep and gr
+    # one-launch Adam iterations (sb_fit_step) over the shards == the same iterations on the whole data on one GPU;
+    # parameters bitwise equal across ranks after every step
+    fit = FitStepper(lib, xs, dxs, "adam", lr=1e-2, w_l1=1e-3)
+    fit.load(Xit, mt)
+    losses = [float(fit.step()) for _ in range(6)]
+    xg = [torch.zeros_like(fit.xi) for _ in range(world)]
+    dist.all_gather(xg, fit.xi)
+    fit_same = all(torch.equal(xg[0], q) for q in xg)
+    xi1 = Xit.clone().contiguous(); st1 = native.fit_state(lib, dev); l1 = []
+    xf, dxf = torch.from_numpy(x).to(dev), torch.from_numpy(dx).to(dev)
+    for it in range(6):
+        l, _, _ = native.fit_step(xf, dxf, xi1, mt, lib, "adam", 1e-2, w_l1=1e-3, state=st1, w_resident=False)
+        l1.append(float(l))
+    e5 = max(abs(a - b) / abs(b) for a, b in zip(losses, l1))
+    e6 = float((fit.xi - xi1).abs().max() / xi1.abs().max())
+    fit_ok = fit_same and e5 < 1e-5 and e6 < 1e-5
+    good = e1 < 1e-6 and e2 < 1e-6 and e3 < 1e-5 and e4 < 1e-5 and same and rep and gr and fit_ok
     ok = ok and good
     if rank == 0:
-        print(f"d={d} p={p}: vs nccl {e1:.1e}/{e2:.1e} vs single {e3:.1e}/{e4:.1e} ranks-bitwise-equal={same} repeat={rep} graph={gr} -> {'OK' if good else 'FAIL'}")
+        print(f"d={d} p={p}: vs nccl {e1:.1e}/{e2:.1e} vs single {e3:.1e}/{e4:.1e} ranks-bitwise-equal={same} repeat={rep} graph={gr} fit: ranks-equal={fit_same} loss {e5:.1e} xi {e6:.1e} -> {'OK' if good else 'FAIL'}")
 t = torch.tensor([1 if ok else 0], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0:
     print("PEER TEST", "PASSED" if int(t) == 1 else "FAILED")
