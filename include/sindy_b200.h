@@ -142,13 +142,14 @@ int sb_closure(const float* x, const float* dx, int64_t n, const sb_library* lib
                void* workspace, int64_t workspace_bytes, void* stream);
 
 /* sb_closure over samples sharded across `world` GPUs of one node, with the all-reduce INSIDE the kernel: the last
- * block of every rank pushes its d·K+2 totals into every rank's symmetric buffer with peer stores over NVLink,
- * raises an epoch flag, waits for all ranks' flags and adds the slots in rank order, then writes the GLOBAL loss and
- * gradient (identical bits on every rank) — no collective launch. peer_bufs: host array of `world` device pointers
- * (peer-mapped, e.g. torch symmetric memory), each at least sb_peer_buffer_bytes(lib, world) bytes and zero-filled
- * before the first call; epoch_dev: a zero-initialised device uint32 owned by this rank. Every rank must make the
- * same sequence of calls. Only the specialised (fused) libraries are supported: SB_ERR_UNSUPPORTED otherwise.
- * packed_out receives the GLOBAL sums. A lost peer makes the kernel give up after ~2 s instead of hanging. */
+ * block of every rank sends each of its d·K+2 totals as one self-validating 16-byte line {lo32, epoch, hi32, epoch}
+ * with a single peer store over NVLink into every rank's symmetric buffer, polls the lines of its own buffer until the
+ * epochs of all senders match and adds them in rank order, then writes the GLOBAL loss and gradient (identical bits
+ * on every rank) — no collective launch, no fence, one NVLink one-way latency. peer_bufs: host array of `world` device
+ * pointers (peer-mapped, e.g. torch symmetric memory), each at least sb_peer_buffer_bytes(lib, world) bytes and
+ * zero-filled before the first call; epoch_dev: a zero-initialised device uint32 owned by this rank. Every rank must
+ * make the same sequence of calls. Only the specialised (fused) libraries are supported: SB_ERR_UNSUPPORTED
+ * otherwise. packed_out receives the GLOBAL sums. A lost peer makes the kernel give up after ~2 s instead of hanging. */
 int sb_closure_peer(const float* x, const float* dx, int64_t n, const sb_library* lib, const float* xi,
                     const float* mask, double w_l1, double* packed_out, float* loss_out, float* grad_out,
                     void* workspace, int64_t workspace_bytes, const void* const* peer_bufs, int world, int rank,

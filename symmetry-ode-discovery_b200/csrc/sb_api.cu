@@ -248,7 +248,7 @@ int64_t sb_peer_buffer_bytes(const sb_library* lib, int world) {
   int s = build_table(lib, &t);
   if (s != SB_OK) return s;
   if (world < 1 || world > SB_MAX_PEERS) return SB_ERR_INVALID;
-  return (int64_t)2 * world * ((int64_t)t.d * t.K + 2) * 8 + (int64_t)2 * world * 8;
+  return (int64_t)2 * world * ((int64_t)t.d * t.K + 2) * 16;   // [2 parities][world senders][d*K+2 lines of 16 B]
 }
 
 int sb_closure_peer(const float* x, const float* dx, int64_t n, const sb_library* lib, const float* xi,

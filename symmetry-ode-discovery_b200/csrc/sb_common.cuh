@@ -219,7 +219,7 @@ int step_epilogue(const double* packed, const LibTab& t, const float* xi, const 
 int mask_mul(const float* xi, const float* mask, float* dst, int count, cudaStream_t s);
 
 // in-kernel all-reduce over peer-mapped symmetric buffers (one per rank; NVLink P2P). Layout of every buffer:
-// [2 parities][world slots][d*K + 2 doubles], then [2][world] 64-bit epoch flags. `epoch` is a local device
+// [2 parities][world senders][d*K + 2 lines of 16 bytes {lo32, epoch, hi32, epoch}]. `epoch` is a local device
 // counter the kernel advances itself (CUDA-graph replay safe).
 struct PeerArgs {
   int world = 0;

@@ -444,45 +444,44 @@ fused_step_kernel(FusedArgs a) {
   __syncthreads();
   stamp(a.trace, 4);
 
-  // ---- all-reduce across GPUs inside the kernel (no NCCL launch): each rank's last block pushes its NV+1 totals
-  // into slot [parity][rank] of EVERY rank's symmetric buffer with plain peer stores over NVLink, publishes a
-  // per-(parity, rank) epoch flag with a system-scope release store, waits for the flags of all ranks in its OWN
-  // buffer, and adds the slots in rank order (identical bits on every rank). Two parities suffice: a rank can run
-  // at most one step ahead, because finishing step e+1 needs every peer's flag e+1, which is only written after
-  // that peer has read the slots of step e.
+  // ---- all-reduce across GPUs inside the kernel (no NCCL launch), low-latency protocol: every value travels as one
+  // 16-byte line {lo32, epoch, hi32, epoch} written with a single peer store over NVLink into slot [parity][sender] of
+  // EVERY rank's symmetric buffer. A line validates itself (each 8-byte half carries the epoch), so there is no fence
+  // and no separate flag: the receiver polls the lines of its OWN buffer until both epochs match and adds the senders
+  // in rank order (identical bits on every rank). One NVLink one-way latency instead of store + system fence + flag.
+  // Two parities suffice: a rank can run at most one step ahead, because finishing step e+1 needs every peer's lines
+  // of e+1, which a peer only sends after it has read the lines of step e.
   if (a.peer.world > 1) {
     constexpr int NVX = C::NV + 1;
+    static_assert(NVX <= C::kThreads, "one exchanged value per thread");
     const int world = a.peer.world, rank = a.peer.rank;
-    const unsigned long long epoch = (unsigned long long)(*a.peer.epoch) + 1ull;
-    const int par = (int)(epoch & 1ull);
-    for (int r = 0; r < world; ++r) {
-      double* dst = a.peer.buf[r] + (size_t)(par * world + rank) * NVX;
-      for (int e = tid; e < NVX; e += C::kThreads) dst[e] = fin[e];
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (tid < world) {
-      unsigned long long* f = reinterpret_cast<unsigned long long*>(a.peer.buf[tid] + (size_t)2 * world * NVX) +
-                              (par * world + rank);
-      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(epoch) : "memory");
-    }
-    if (tid < world) {
-      const unsigned long long* f =
-          reinterpret_cast<const unsigned long long*>(a.peer.buf[rank] + (size_t)2 * world * NVX) + (par * world + tid);
-      const long long t0 = clock64();
-      unsigned long long seen = 0;
-      do {
-        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(f) : "memory");
-      } while (seen < epoch && (clock64() - t0) < 4000000000ll);   // ~2 s: never hang the GPU on a lost peer
-    }
-    __syncthreads();
-    const double* mine = a.peer.buf[rank] + (size_t)par * world * NVX;
-    for (int e = tid; e < NVX; e += C::kThreads) {
+    const unsigned int epoch = *a.peer.epoch + 1u;
+    const int par = (int)(epoch & 1u);
+    if (tid < NVX) {
+      const unsigned long long bits = (unsigned long long)__double_as_longlong(fin[tid]);
+      const unsigned int lo = (unsigned int)bits, hi = (unsigned int)(bits >> 32);
+      for (int r = 0; r < world; ++r) {
+        uint4* dst = reinterpret_cast<uint4*>(a.peer.buf[r]) + (size_t)(par * world + rank) * NVX + tid;
+        asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(lo), "r"(epoch), "r"(hi),
+                     "r"(epoch)
+                     : "memory");
+      }
       double v = 0.0;
-      for (int r = 0; r < world; ++r) v += mine[(size_t)r * NVX + e];
-      fin[e] = v;
+      const long long t0 = clock64();
+      for (int r = 0; r < world; ++r) {
+        const uint4* src = reinterpret_cast<const uint4*>(a.peer.buf[rank]) + (size_t)(par * world + r) * NVX + tid;
+        unsigned int q0, q1, q2, q3;
+        do {
+          asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(q0), "=r"(q1), "=r"(q2), "=r"(q3)
+                       : "l"(src)
+                       : "memory");
+        } while ((q1 != epoch || q3 != epoch) && (clock64() - t0) < 4000000000ll);   // ~2 s: never hang on a lost peer
+        v += __longlong_as_double((long long)(((unsigned long long)q2 << 32) | (unsigned long long)q0));
+      }
+      fin[tid] = v;
     }
-    if (tid == 0) *a.peer.epoch = (unsigned int)epoch;
+    if (tid == 0) *a.peer.epoch = epoch;
     __syncthreads();
   }
   const double n_total = fin[C::NV];

@@ -244,8 +244,10 @@ class FitStepper:
             if self.peer is None:
                 raise RuntimeError("FitStepper over several ranks needs the peer exchange (symmetric memory); use "
                                    "ShardedTrainStep for the NCCL path")
+        self.loss_hist = torch.zeros(64, dtype=torch.float32, device=dev)
         self._use_graph = use_graph
-        self._graph = None
+        self._graphs = {}
+        self._warm = False
         self._loaded = False
 
     def load(self, xi: torch.Tensor, mask: Optional[torch.Tensor] = None, reset_state: bool = False):
@@ -257,36 +259,74 @@ class FitStepper:
         native.load_w(self.xi, self.mask, self.lib)
         self._loaded = True
 
-    def _launch(self):
+    def _launch(self, loss=None):
         p = self.peer
         native.fit_step(self.x, self.dx, self.xi, self.mask, self.lib, self.kind, self.lr, self.betas, self.eps,
-                        self.w_mse, self.w_l1, state=self.state, w_resident=True, packed=self.packed, loss=self.loss,
-                        grad=self.grad, peer_ptrs=p.ptrs if p else None, rank=p.rank if p else 0,
-                        epoch=p.epoch if p else None)
+                        self.w_mse, self.w_l1, state=self.state, w_resident=True, packed=self.packed,
+                        loss=self.loss if loss is None else loss, grad=self.grad,
+                        peer_ptrs=p.ptrs if p else None, rank=p.rank if p else 0, epoch=p.epoch if p else None)
+
+    def _capture(self, n_iters):
+        """CUDA graph of n_iters consecutive iterations; iteration i writes its loss to loss_hist[i] (n_iters > 1)."""
+        if not self._warm:
+            # first-call attribute / occupancy queries and the workspace allocation must not happen under capture;
+            # the warm-up iteration is undone (parameters, Adam state) — every rank does the same, so the peer epoch
+            # stays consistent
+            keep_xi, keep_state = self.xi.clone(), self.state.clone()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._launch()
+            torch.cuda.current_stream().wait_stream(side)
+            self.xi.copy_(keep_xi)
+            self.state.copy_(keep_state)
+            native.load_w(self.xi, self.mask, self.lib)
+            self._warm = True
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            if n_iters == 1:
+                self._launch()
+            else:
+                for i in range(n_iters):
+                    self._launch(self.loss_hist[i])
+        return g
 
     def step(self):
+        """One iteration; returns the (static) loss tensor: the value at the parameters BEFORE the update."""
         if not self._loaded:
             raise ValueError("call load(xi, mask) first")
         if not self._use_graph:
             self._launch()
             return self.loss
-        if self._graph is None:
-            # capture only: nothing inside the graph has run yet, so parameters, Adam state and the peer epoch are
-            # exactly what load() left (the workspace and the occupancy query are warmed by load_w / earlier calls)
-            keep_xi, keep_state = self.xi.clone(), self.state.clone()
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                self._launch()   # warm-up outside capture (first-call attribute/occupancy queries)
-            torch.cuda.current_stream().wait_stream(side)
-            self.xi.copy_(keep_xi)
-            self.state.copy_(keep_state)
-            native.load_w(self.xi, self.mask, self.lib)
-            self._graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self._graph):
-                self._launch()
-        self._graph.replay()
+        if 1 not in self._graphs:
+            self._graphs[1] = self._capture(1)
+        self._graphs[1].replay()
         return self.loss
+
+    def run(self, n_iters: int, unroll: int = 10):
+        """n_iters iterations with no host involvement in between: graphs of `unroll` back-to-back launches (kernels
+        inside one graph follow each other ~1 us apart, separate replays ~5 us). Returns the loss tensor of the last
+        iteration; `loss_hist[:unroll]` holds the losses of the last full group."""
+        if not self._loaded:
+            raise ValueError("call load(xi, mask) first")
+        if not self._use_graph:
+            for _ in range(n_iters):
+                self._launch()
+            return self.loss
+        unroll = max(1, min(int(unroll), self.loss_hist.numel()))
+        full, rest = divmod(int(n_iters), unroll)
+        last = self.loss
+        if full and unroll > 1:
+            if unroll not in self._graphs:
+                self._graphs[unroll] = self._capture(unroll)
+            for _ in range(full):
+                self._graphs[unroll].replay()
+            last = self.loss_hist[unroll - 1]
+        elif full:
+            rest += full
+        for _ in range(rest):
+            last = self.step()
+        return last
 
 
 class HostStreamedStep:

@@ -145,3 +145,12 @@ def test_fit_stepper_graph_replay_matches_eager():
         assert abs(float(loss) - ref_losses[it]) <= 2e-5 * abs(ref_losses[it]), it
         assert rel(st.xi, ref_params[it]) < 2e-5, (it, rel(st.xi, ref_params[it]))
     assert int(st.state[-1:].view(torch.int32)) == 12
+    # run(): groups of `unroll` iterations per graph replay (+ single-step remainder) give the same trajectory
+    st2 = FitStepper(lib, x, dx, "adam", lr=1e-2, w_l1=1e-3)
+    st2.load(Xi0, masks[0])
+    last = st2.run(6, unroll=4)
+    assert rel(st2.xi, ref_params[5]) < 2e-5
+    assert abs(float(last) - ref_losses[5]) <= 2e-5 * abs(ref_losses[5])
+    st2.load(Xi0, masks[0], reset_state=True)
+    st2.run(4, unroll=4)
+    np.testing.assert_allclose(st2.loss_hist[:4].cpu().numpy(), ref_losses[:4], rtol=2e-5)
