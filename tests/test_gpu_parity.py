@@ -266,9 +266,11 @@ def test_golden_wsindy(nat, golden):
     wr = sindy.WSINDyWrapper(reg, t, t_max, device="cuda")
     assert np.array_equal(wr.V[:, ::40].cpu().numpy(), g["V"]) or rel(wr.V[:, ::40], g["V"]) < 1e-6
     G, b = wr.integrals(traj)
-    assert rel(G, g["G"]) < 1e-5 and rel(b, g["b"]) < 1e-5, (rel(G, g["G"]), rel(b, g["b"]))
+    # north_star tolerance (1e-4). Usually ~2e-6; the phase k·pi·t/T reaches 157 rad, where one fp32 ulp of the argument
+    # moves sin() by 1.5e-5, and the golden G itself is an fp32 GEMM over 8000 terms — 5e-5 has been seen on one box.
+    assert rel(G, g["G"]) < 1e-4 and rel(b, g["b"]) < 1e-4, (rel(G, g["G"]), rel(b, g["b"]))
     Go, bo = O.wsindy_integrals(g["traj"], dt, t_max, 3)
-    assert rel(G, Go) < 1e-5 and rel(b, bo) < 1e-5
+    assert rel(G, Go) < 1e-4 and rel(b, bo) < 1e-4, (rel(G, Go), rel(b, bo))
     for w in (0.05, 0.01):
         tag = f"w{int(w * 100)}"
         reg = sindy.SINDyRegression(2, 3, False, False, threshold=0.075, device="cuda", constrain_constant=True)
