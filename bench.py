@@ -505,6 +505,19 @@ def extras(native, dev, peaks, fp32_peak):
                                             "fp32_tflops": flop_sym * n / (ms * 1e-3) / 1e12,
                                             "fp32_frac": flop_sym * n / (ms * 1e-3) / 1e12 / fp32_peak,
                                             "bytes_per_sample": 36}
+    # the same objective with the Gram matrix of the fixed data set formed ONCE per fit (moment kernel, timed separately)
+    # and the regulariser + gradient evaluated as a quadratic form in the epilogue of the one-launch iteration
+    from sindy_b200.dist import FitStepper
+    from sindy_b200 import symreg
+    ms_gram = timed(lambda: symreg.gram(x, lib))
+    fs = FitStepper(lib, x, dx, "adam", lr=1e-6, sym_gens=list(so3), w_sym=0.1)
+    fs.load(W, torch.ones_like(W))
+    fs.run(10, 10)
+    ms = timed(lambda: fs.run(10, 10)) / 10
+    out["fit_step_C5_with_so3_symreg_cached_gram"] = {
+        "samples_per_s": n / (ms * 1e-3), "ms": ms, "gram_once_per_fit_ms": ms_gram,
+        "note": "one launch per Adam iteration; w_sym*w'Hw and 2Hw evaluated by the kernel's last block, H from the Gram of the data set"}
+    del fs
     o = torch.empty(lib.step_out_len(12), dtype=torch.float64, device=dev)
     ms = timed(lambda: native.train_step(x, dx, None, lib, 12, out=o))
     out["stlsq_data_pass_C5_gram_and_b"] = {"samples_per_s": n / (ms * 1e-3), "ms": ms,

@@ -183,6 +183,11 @@ typedef struct {
   float eps;
   float w_mse;   /* w_sindy_x */
   float w_l1;    /* w_sindy_reg */
+  float w_sym;   /* weight of the linear Lie-derivative regulariser (0 = none) */
+  const float* sym_quad; /* device, (d·K)×(d·K) fp32 symmetric H (16-byte aligned) with
+                            Σ_v Σ_n ‖J_h(z_n)(v z_n) − v h(z_n)‖² = wᵀHw, w = vec(Ξ⊙mask) row-major (`train.py:503-507`,
+                            intended formula; H = Σ_v L_vᵀ(I_d⊗ΘᵀΘ)L_v is a constant of the data set, built once per fit);
+                            NULL = no regulariser. Loss and gradient gain w_sym·wᵀHw and w_sym·2Hw⊙mask. */
 } sb_fit_options;
 int sb_fit_step(const float* x, const float* dx, int64_t n, const sb_library* lib, float* xi, const float* mask,
                 const sb_fit_options* opt, float* opt_state, double* packed_out, float* loss_out, float* grad_out,

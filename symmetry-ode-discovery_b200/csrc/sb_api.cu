@@ -318,6 +318,10 @@ int sb_fit_step(const float* x, const float* dx, int64_t n, const sb_library* li
     fa.m = opt_state; fa.v = opt_state + dk; fa.step = reinterpret_cast<unsigned int*>(opt_state + 2 * dk);
   }
   fa.w_resident = (call_flags & SB_FIT_W_RESIDENT) != 0;
+  if (opt->sym_quad && opt->w_sym != 0.f) {
+    if (reinterpret_cast<uintptr_t>(opt->sym_quad) & 15u) { set_error("sym_quad must be 16-byte aligned"); return SB_ERR_INVALID; }
+    fa.sym_H = opt->sym_quad; fa.w_sym = (double)opt->w_sym;
+  }
   return fused_train_step(x, dx, n, t, xi, mask, flags, packed_out, &co, world > 1 ? &pa : nullptr, ws, ws_bytes,
                           (cudaStream_t)stream, &fa);
 }

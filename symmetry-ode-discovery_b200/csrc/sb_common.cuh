@@ -211,6 +211,8 @@ struct FitArgs {
   float* v = nullptr;
   unsigned int* step = nullptr; // Adam step counter (device)
   bool w_resident = false;      // the constant bank already holds Ξ⊙mask (left there by the previous fit step)
+  const float* sym_H = nullptr; // quadratic form of the linear Lie-derivative regulariser ((d·K)² fp32) or NULL
+  double w_sym = 0.0;
 };
 // loss / gradient from (all-reduced) packed sums; one tiny launch
 int step_epilogue(const double* packed, const LibTab& t, const float* xi, const float* mask, double w_l1,

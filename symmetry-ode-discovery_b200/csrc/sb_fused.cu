@@ -168,6 +168,9 @@ struct FusedArgs {
   // into the constant bank for the NEXT launch, so a whole training iteration is this one kernel
   FitArgs fit;
   float* w_const;     // device address of the packed constant slot (c_w2)
+  // optional linear Lie-derivative regulariser as a quadratic form of w = vec(Ξ⊙mask): w_sym·wᵀHw (sb_fit_options)
+  const float* sym_H; // (d·K)² fp32, symmetric, row-major
+  double w_sym;
   unsigned long long* trace;  // debug: 16 globaltimer stamps per CTA (sb_debug_trace), NULL in production
   // optional in-kernel all-reduce over peer memory (NVLink P2P stores + flags): see the final phase
   PeerArgs peer;
@@ -509,13 +512,58 @@ fused_step_kernel(FusedArgs a) {
       step_size = (float)((double)a.fit.lr / (1.0 - powi((double)a.fit.beta1, t)));
       bc2_sqrt = (float)sqrt(1.0 - powi((double)a.fit.beta2, t));
     }
-    double l1 = 0.0;
+    // linear Lie-derivative regulariser (`train.py:503-507`, intended formula) for a FIXED data set: with G = ΘᵀΘ
+    // known, Σ_v Σ_n ‖J_h(z_n)(v z_n) − v h(z_n)‖² = wᵀHw is an exact quadratic form of w = vec(Ξ⊙mask); H is built
+    // once per fit (symreg.quadratic_form). Here: hw = H·w by 256 threads — column quads × row groups, every load
+    // of a thread in flight at once — then loss += w_sym·wᵀhw and grad += w_sym·2·hw⊙mask.
+    double sym_hw = 0.0, sym_w = 0.0;
+    if (a.sym_H) {
+      constexpr int DK = D * C::K;
+      float* wsm = reinterpret_cast<float*>(smem_raw);          // the tile ring is idle: w, then the partial products
+      if (tid < DK) wsm[tid] = ep_xi * ep_mk;
+      __syncthreads();
+      if constexpr (DK % 4 == 0) {
+        constexpr int NCQ = DK / 4, NRG = C::kThreads / NCQ, ROWS = (DK + NRG - 1) / NRG;
+        float* part = wsm + ((DK + 3) & ~3);                     // [NRG][DK]
+        const int rg = tid / NCQ, cq = tid % NCQ;
+        if (rg < NRG) {
+          const float4* Hq = reinterpret_cast<const float4*>(a.sym_H);
+          float4 h[ROWS];
+          static_for<0, ROWS>([&](auto rc) {
+            constexpr int r = rc;
+            const int j = rg + r * NRG;
+            h[r] = j < DK ? __ldg(Hq + (size_t)j * NCQ + cq) : make_float4(0.f, 0.f, 0.f, 0.f);
+          });
+          float4 sacc = make_float4(0.f, 0.f, 0.f, 0.f);
+          static_for<0, ROWS>([&](auto rc) {
+            constexpr int r = rc;
+            const int j = rg + r * NRG;
+            const float wj = j < DK ? wsm[j] : 0.f;
+            sacc.x = fmaf(h[r].x, wj, sacc.x); sacc.y = fmaf(h[r].y, wj, sacc.y);
+            sacc.z = fmaf(h[r].z, wj, sacc.z); sacc.w = fmaf(h[r].w, wj, sacc.w);
+          });
+          reinterpret_cast<float4*>(part + rg * DK)[cq] = sacc;
+        }
+        __syncthreads();
+        if (tid < DK) {
+          for (int g = 0; g < NRG; ++g) sym_hw += (double)part[g * DK + tid];
+        }
+      } else {
+        if (tid < DK) {   // small libraries whose d·K is not a multiple of 4: one column per thread (H is symmetric)
+          for (int j = 0; j < DK; ++j) sym_hw += (double)__ldg(a.sym_H + (size_t)j * DK + tid) * (double)wsm[j];
+        }
+      }
+      if (tid < DK) sym_w = (double)wsm[tid];
+    }
+    double l1 = 0.0, lsym = 0.0;
     if (ep_on) {
       const int e = tid;
       const float xi = ep_xi, mk = ep_mk;
       l1 = fabs((double)xi);
+      lsym = sym_w * sym_hw;
       const double sgn = (xi > 0.f) ? 1.0 : ((xi < 0.f) ? -1.0 : 0.0);
-      const float g = (float)(fin[e] * (2.0 / denom) * a.w_mse * (double)mk + a.w_l1 * sgn);
+      const float g = (float)(fin[e] * (2.0 / denom) * a.w_mse * (double)mk + a.w_l1 * sgn +
+                              a.w_sym * 2.0 * sym_hw * (double)mk);
       if (a.grad_out) a.grad_out[e] = g;
       if (a.fit.kind != SB_OPT_NONE) {
         float xn;
@@ -536,14 +584,15 @@ fused_step_kernel(FusedArgs a) {
       }
     }
     l1 = warp_sum(l1);
-    __shared__ double l1w[C::kWarps];
-    if (lane == 0) l1w[wid] = l1;
+    lsym = warp_sum(lsym);
+    __shared__ double l1w[C::kWarps], lsw[C::kWarps];
+    if (lane == 0) { l1w[wid] = l1; lsw[wid] = lsym; }
     __syncthreads();
     if (tid == 0) {
       if (a.loss_out) {
-        double t = 0.0;
-        for (int wq = 0; wq < C::kWarps; ++wq) t += l1w[wq];
-        *a.loss_out = (float)(a.w_mse * fin[C::NV - 1] / denom + a.w_l1 * t);
+        double t = 0.0, ts = 0.0;
+        for (int wq = 0; wq < C::kWarps; ++wq) { t += l1w[wq]; ts += lsw[wq]; }
+        *a.loss_out = (float)(a.w_mse * fin[C::NV - 1] / denom + a.w_l1 * t + a.w_sym * ts);
       }
       if (a.fit.kind == SB_OPT_ADAM) *a.fit.step = ep_step + 1u;
     }
@@ -682,13 +731,14 @@ int run_fused(const float* x, const float* dx, int64_t n, const float* w, const 
     }
     if (fit && fit->kind != SB_OPT_NONE) {
       a.fit = *fit;
+      a.sym_H = fit->sym_H; a.w_sym = fit->w_sym;
       st = const_slot(&a.w_const);
       if (st != SB_OK) return st;
     }
     if (peer) a.peer = *peer;
     st = launch_fused<D, P, LEFT_RESIDUAL>(a, ws, ws_bytes, s);
     if (st != SB_OK) return st;
-    a.loss_out = nullptr; a.grad_out = nullptr; a.peer = PeerArgs{}; a.fit = FitArgs{};
+    a.loss_out = nullptr; a.grad_out = nullptr; a.peer = PeerArgs{}; a.fit = FitArgs{}; a.sym_H = nullptr;
   }
   if (flags & SB_STEP_B) {
     // the ΘᵀẊ section follows the (optional) gradient and Gram sections of the packed layout

@@ -227,8 +227,18 @@ class FitStepper:
 
     def __init__(self, lib: Library, x: torch.Tensor, dx: torch.Tensor, kind: str = "adam", lr: float = 1e-3,
                  betas=(0.9, 0.999), eps: float = 1e-8, w_mse: float = 1.0, w_l1: float = 0.0, group=None,
-                 use_graph: bool = True, use_peer: bool = True):
+                 use_graph: bool = True, use_peer: bool = True, sym_gens=None, w_sym: float = 0.0):
         self.lib, self.x, self.dx = lib, x, dx
+        # linear Lie-derivative regulariser (`train.py:503-507`): the Gram matrix of the (fixed) data set is formed
+        # once — one pass of the moment kernel per rank and one all-reduce — and turned into the quadratic form H;
+        # every iteration then evaluates w_sym·wᵀHw and its gradient inside the kernel's epilogue
+        self.sym_quad, self.w_sym = None, float(w_sym)
+        if sym_gens is not None and len(sym_gens) > 0 and w_sym != 0.0:
+            from . import symreg
+            G = symreg.gram(x, lib).clone()
+            if _world(group) > 1:
+                dist.all_reduce(G, op=dist.ReduceOp.SUM, group=group)
+            self.sym_quad = symreg.quadratic_form(lib, sym_gens, G).to(torch.float32).contiguous()
         self.kind, self.lr, self.betas, self.eps, self.w_mse, self.w_l1 = kind, lr, betas, eps, w_mse, w_l1
         dev = x.device
         d, K = lib.dim, lib.K
@@ -264,7 +274,8 @@ class FitStepper:
         native.fit_step(self.x, self.dx, self.xi, self.mask, self.lib, self.kind, self.lr, self.betas, self.eps,
                         self.w_mse, self.w_l1, state=self.state, w_resident=True, packed=self.packed,
                         loss=self.loss if loss is None else loss, grad=self.grad,
-                        peer_ptrs=p.ptrs if p else None, rank=p.rank if p else 0, epoch=p.epoch if p else None)
+                        peer_ptrs=p.ptrs if p else None, rank=p.rank if p else 0, epoch=p.epoch if p else None,
+                        sym_quad=self.sym_quad, w_sym=self.w_sym)
 
     def _capture(self, n_iters):
         """CUDA graph of n_iters consecutive iterations; iteration i writes its loss to loss_hist[i] (n_iters > 1)."""

@@ -33,7 +33,7 @@ class _CLibrary(ctypes.Structure):
 
 class _CFitOptions(ctypes.Structure):
     _fields_ = [("kind", c_int32), ("lr", c_float), ("beta1", c_float), ("beta2", c_float), ("eps", c_float),
-                ("w_mse", c_float), ("w_l1", c_float)]
+                ("w_mse", c_float), ("w_l1", c_float), ("w_sym", c_float), ("sym_quad", c_void_p)]
 
 
 # every symbol include/sindy_b200.h declares: name -> (restype, argtypes)
@@ -369,10 +369,11 @@ def fit_step(x: torch.Tensor, dx: torch.Tensor, xi: torch.Tensor, mask: Optional
              w_l1: float = 0.0, state: Optional[torch.Tensor] = None, w_resident: bool = False,
              packed: Optional[torch.Tensor] = None, loss: Optional[torch.Tensor] = None,
              grad: Optional[torch.Tensor] = None, peer_ptrs=None, rank: int = 0,
-             epoch: Optional[torch.Tensor] = None):
+             epoch: Optional[torch.Tensor] = None, sym_quad: Optional[torch.Tensor] = None, w_sym: float = 0.0):
     """One iteration of the Adam (or SGD) loop `train.py:512-530` in ONE launch: loss and dL/dΞ at the current
     parameters, then `xi` (fp32 CUDA, contiguous) is advanced IN PLACE. Returns (loss, grad, packed). `state`
-    = fit_state(lib) for Adam. With peer_ptrs the samples are sharded over the ranks (see closure_peer)."""
+    = fit_state(lib) for Adam. With peer_ptrs the samples are sharded over the ranks (see closure_peer).
+    sym_quad (symreg.quadratic_form) adds w_sym × the linear Lie-derivative regulariser of the data set."""
     xf = _flat(_f32c(x, "x"), lib.dim, "x")
     dxf = _flat(_f32c(dx, "dx"), lib.dim, "dx")
     _require_cuda(xi, "xi")
@@ -392,7 +393,13 @@ def fit_step(x: torch.Tensor, dx: torch.Tensor, xi: torch.Tensor, mask: Optional
         loss = torch.empty((), dtype=torch.float32, device=dev)
     if grad is None:
         grad = torch.empty(d, K, dtype=torch.float32, device=dev)
-    opt = _CFitOptions(kinds[kind], float(lr), float(betas[0]), float(betas[1]), float(eps), float(w_mse), float(w_l1))
+    if sym_quad is not None:
+        dk = lib.dim * lib.K
+        if (not sym_quad.is_cuda or sym_quad.dtype != torch.float32 or not sym_quad.is_contiguous()
+                or tuple(sym_quad.shape) != (dk, dk)):
+            raise ValueError("`sym_quad` must be a contiguous CUDA float32 (d·K, d·K) matrix (symreg.quadratic_form)")
+    opt = _CFitOptions(kinds[kind], float(lr), float(betas[0]), float(betas[1]), float(eps), float(w_mse), float(w_l1),
+                       float(w_sym) if sym_quad is not None else 0.0, _ptr(sym_quad))
     world = len(peer_ptrs) if peer_ptrs else 1
     arr = (c_void_p * world)(*[int(p) for p in peer_ptrs]) if world > 1 else None
     ws = _workspace(lib, dev)

@@ -60,6 +60,26 @@ def lie_loss_from_gram(G: torch.Tensor, W: torch.Tensor, gens: Sequence[torch.Te
     return loss
 
 
+def quadratic_form(lib: Library, gens: Sequence[torch.Tensor], G: torch.Tensor) -> torch.Tensor:
+    """H ((d·K)×(d·K), fp64, symmetric) with Σ_v tr(A_v G A_vᵀ) = wᵀ H w for w = vec(W) row-major:
+    vec(W M_v − v W) = (I_d ⊗ M_vᵀ − v ⊗ I_K) w =: L_v w, so H = Σ_v L_vᵀ (I_d ⊗ G) L_v. G = ΘᵀΘ of the (whole,
+    all-reduced) data set makes H a constant of the fit: sb_fit_step evaluates the regulariser and its gradient 2Hw
+    in the fused kernel's epilogue with no further data pass."""
+    d, K = lib.dim, lib.K
+    dev = G.device
+    Gd = G.to(torch.float64)
+    eye_d = torch.eye(d, dtype=torch.float64, device=dev)
+    eye_K = torch.eye(K, dtype=torch.float64, device=dev)
+    IG = torch.kron(eye_d, Gd)
+    H = torch.zeros(d * K, d * K, dtype=torch.float64, device=dev)
+    for v in gens:
+        v = torch.as_tensor(v).to(dev, torch.float64)
+        M = lie_matrix(lib, v).to(dev)
+        L = torch.kron(eye_d, M.T.contiguous()) - torch.kron(v, eye_K)
+        H = H + L.T @ IG @ L
+    return 0.5 * (H + H.T)
+
+
 def lie_loss_per_sample(z: torch.Tensor, W: torch.Tensor, gens: Sequence[torch.Tensor], lib: Library) -> torch.Tensor:
     """Σ_v ‖J_h(z)(v z) − v h(z)‖² with the CUDA forward / JVP operators (any library)."""
     h = ops.sindy_forward(z, W, lib)

@@ -203,3 +203,26 @@ def test_systems_match_truth_tables(golden):
     g = golden("model")
     for name in ("dosc", "growth", "lv", "selkov"):
         assert np.allclose(systems.SYSTEMS[name]().Xi, g["truth_" + name])
+
+
+def test_lie_regulariser_quadratic_form_equals_gram_form():
+    """symreg.quadratic_form: wᵀHw and 2Hw reproduce Σ_v tr(A_v G A_vᵀ), A_v = W M_v − v W, and its gradient
+    (`train.py:503-507`, intended formula) — host-side algebra, no GPU."""
+    import torch
+    from sindy_b200 import native, symreg
+    for (d, p) in ((2, 3), (3, 3)):
+        lib = native.Library(d, p)
+        K = lib.K
+        g = torch.Generator().manual_seed(d * 10 + p)
+        A = torch.randn(300, K, dtype=torch.float64, generator=g)
+        G = A.T @ A
+        W = torch.randn(d, K, dtype=torch.float64, generator=g).requires_grad_(True)
+        gens = [torch.randn(d, d, dtype=torch.float64, generator=g) for _ in range(3)]
+        Ms = [symreg.lie_matrix(lib, v) for v in gens]
+        loss = symreg.lie_loss_from_gram(G, W, gens, Ms)
+        loss.backward()
+        H = symreg.quadratic_form(lib, gens, G)
+        w = W.detach().reshape(-1)
+        assert torch.equal(H, H.T)
+        assert abs(float(w @ H @ w) - float(loss.detach())) <= 1e-12 * float(loss.detach())
+        assert float((2 * H @ w - W.grad.reshape(-1)).abs().max()) <= 1e-12 * float(W.grad.abs().max())

@@ -154,3 +154,44 @@ def test_fit_stepper_graph_replay_matches_eager():
     st2.load(Xi0, masks[0], reset_state=True)
     st2.run(4, unroll=4)
     np.testing.assert_allclose(st2.loss_hist[:4].cpu().numpy(), ref_losses[:4], rtol=2e-5)
+
+
+@pytest.mark.parametrize("d,p", [(3, 5), (3, 2), (2, 3)])
+def test_fit_step_with_lie_regulariser_in_the_epilogue(d, p, monkeypatch):
+    """One-launch iteration with the linear Lie-derivative regulariser as the quadratic form of the data set's Gram
+    matrix (sb_fit_options.sym_quad) against the eager sequence: fused closure + SINDyRegression.lie_reg_loss (autograd
+    through the Gram form, pinned to the reference golden elsewhere) + torch.optim.Adam."""
+    import sindy
+    from sindy_b200 import native
+    from sindy_b200.dist import FitStepper
+    monkeypatch.setenv("SB_MOMENTS_MIN_SAMPLES", "0")
+    lib = native.Library(d, p)
+    K = lib.K
+    g = torch.Generator(device="cuda").manual_seed(7)
+    n = 50_000
+    x = torch.rand(n, d, device="cuda", generator=g) * 2 - 1
+    dx = torch.randn(n, d, device="cuda", generator=g)
+    gens = []
+    for i in range(d):
+        for j in range(i):
+            v = torch.zeros(d, d, device="cuda"); v[i, j], v[j, i] = 1.0, -1.0
+            gens.append(v)
+    w_sym, w_l1, lr = 1e-5, 1e-3, 1e-2
+    reg = sindy.SINDyRegression(d, p, False, False, threshold=0.05, device="cuda", constrain_constant=True)
+    Xi0 = 0.1 * torch.randn(d, K, device="cuda", generator=g)
+    mask = (torch.rand(d, K, device="cuda", generator=g) > 0.2).float()
+    reg.Xi.data = Xi0.clone()
+    reg.mask.data = mask.clone()
+    opt = torch.optim.Adam(reg.parameters(), lr=lr)
+    ref_losses = []
+    for it in range(8):
+        opt.zero_grad()
+        loss = reg.mse_loss(x, dx) + w_sym * reg.lie_reg_loss(x, gens, method="gram") + w_l1 * reg.Xi.abs().sum()
+        loss.backward()
+        opt.step()
+        ref_losses.append(float(loss))
+    st = FitStepper(lib, x, dx, "adam", lr=lr, w_l1=w_l1, sym_gens=gens, w_sym=w_sym)
+    st.load(Xi0, mask)
+    losses = [float(st.step()) for _ in range(8)]
+    np.testing.assert_allclose(losses, ref_losses, rtol=5e-5)
+    assert rel(st.xi, reg.Xi) < 1e-4, rel(st.xi, reg.Xi)
