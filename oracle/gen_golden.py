@@ -377,8 +377,26 @@ def gen_adam():
     save("adam", **out)
 
 
+def gen_smoothing():
+    """GP smoother + derivative of the data generators (`data_utils/smoothing.py:155-196` num_diff_gp, called from
+    `data_utils/ode.py:43-45`), on small noisy damped-oscillator and Lotka-Volterra batches."""
+    from data_utils.smoothing import num_diff_gp
+    out = {}
+    rng = np.random.default_rng(5)
+    for name, f, dt, T, n_traj, noise, sigma_in in (("dosc", damped_oscillator.dosc, 0.01, 300, 4, 0.2, 0.1),
+                                                    ("lv", lotka.lotka_volterra, 0.02, 200, 3, 0.05, None)):
+        x0 = rng.uniform(0.5, 1.5, (n_traj, 2))
+        x, _ = ref_ode.solve_ode_batch(f, x0, dt=dt, num_steps=T)
+        std = np.std(x, axis=(0, 1))
+        xn = x + rng.standard_normal(x.shape) * noise * std
+        dX, Xs = num_diff_gp(xn.copy(), dt, noise_level=noise, std_base=std, sigma_in=sigma_in)
+        out.update({name + "_x": xn, name + "_std": std, name + "_dt": dt, name + "_noise": noise,
+                    name + "_sigma_in": (np.nan if sigma_in is None else sigma_in), name + "_dX": dX, name + "_X": Xs})
+    save("smoothing", **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["model", "jvp", "stlsq", "wsindy", "rollout", "symmreg", "lbfgs", "adam"]
+    which = sys.argv[1:] or ["model", "jvp", "stlsq", "wsindy", "rollout", "symmreg", "lbfgs", "adam", "smoothing"]
     for w in which:
         globals()["gen_" + w]()

@@ -416,3 +416,31 @@ def odeint(f, x0, t, dt, method='euler', full_traj=False):
         if full_traj:
             traj.append(x)
     return np.stack(traj, axis=0) if full_traj else x
+
+
+# ---------------------------------------------------------------------------------------------------------
+# GP smoother of the data generators  (data_utils/smoothing.py:155-196 num_diff_gp, GPPCA0 :17-152)
+# ---------------------------------------------------------------------------------------------------------
+
+
+def num_diff_gp(x, dt, noise_level, std_base, sigma_in=None, eps=0.001):
+    """x: (T, n_traj, dim) noisy states. Returns (dX, X) like the reference.
+
+    The reference keeps r = n_traj principal components (`smoothing.py:181-182`), i.e. ALL of them, so the factor
+    loading A is a full orthogonal matrix and X_hat = K_new (K + s^2 I)^-1 Y A A^T (`:137-143`) is plain GP regression
+    with the RBF kernel K = s_out^2 exp(-(t_i - t_j)^2 / (2 s_in^2)), s_out = std_base[d], s = noise_level * std_base[d],
+    s_in = sigma_in or dt (`:29-32`); the derivative is the forward difference of the posterior mean over eps = 0.001
+    (`:186-195`)."""
+    x = np.asarray(x, dtype=np.float64)
+    T = x.shape[0]
+    t = np.arange(T) * dt
+    dX, Xs = np.empty_like(x), np.empty_like(x)
+    for d in range(x.shape[2]):
+        s_out, s = std_base[d], noise_level * std_base[d]
+        s_in = (t[1] - t[0]) if sigma_in is None else sigma_in
+        K = s_out ** 2 * np.exp(-(t[:, None] - t[None, :]) ** 2 / (2 * s_in ** 2))
+        K2 = s_out ** 2 * np.exp(-((t + eps)[:, None] - t[None, :]) ** 2 / (2 * s_in ** 2))
+        alpha = np.linalg.solve(K + s ** 2 * np.eye(T), x[:, :, d])
+        Xs[:, :, d] = K @ alpha
+        dX[:, :, d] = (K2 @ alpha - Xs[:, :, d]) / eps
+    return dX, Xs

@@ -65,7 +65,8 @@ def solve_ode_batch(ode, x0, dt=0.002, num_steps=2000, solver='rk4', device=None
 def gen_data(ode, init_fn, n_ics=1000, dt=0.002, num_steps=2000, subsample_rate=1, noise=0.0,
              multiplicative_noise=False, smoothing=None, **kwargs):
     """Trajectories (n_ics, num_steps/subsample_rate, dim) and derivatives, as the reference's gen_data
-    (`data_utils/ode.py:30-49`): noise and finite differences on the host; GP smoothing is out of scope."""
+    (`data_utils/ode.py:30-49`): noise and finite differences on the host; `smoothing='gp'` runs the GP smoother of
+    data_utils/smoothing.py on the GPU (needs kwargs['gp_sigma_in'] like the reference)."""
     x0 = init_fn(n_ics)
     x, dx = solve_ode_batch(ode, x0, dt=dt, num_steps=num_steps)
     if noise > 0:
@@ -76,9 +77,10 @@ def gen_data(ode, init_fn, n_ics=1000, dt=0.002, num_steps=2000, subsample_rate=
             x += np.random.randn(*x.shape) * noise * x_std
         if smoothing is None:
             dx[:-1, :] = np.diff(x, axis=0) / dt
-        else:
-            raise NotImplementedError("GP smoothing (data_utils/smoothing.py) is outside the B200 hot path; "
-                                      "smooth with the reference and feed the .pt files")
+        elif smoothing == 'gp':
+            from .smoothing import num_diff_gp
+            print('Smoothing with Gaussian process...')
+            dx, x = num_diff_gp(x, dt, noise_level=noise, std_base=x_std, sigma_in=kwargs['gp_sigma_in'])
     x = np.transpose(x[::subsample_rate], (1, 0, 2))
     dx = np.transpose(dx[::subsample_rate], (1, 0, 2))
     return x, dx

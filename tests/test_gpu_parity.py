@@ -493,3 +493,18 @@ def test_fused_variants_agree(nat):
         assert np.abs(r - res[0]).max() / np.abs(res[0]).max() < 1e-6
     assert np.array_equal(res[0], res[1])      # 15 and 47 differ only in when a sample is read from smem: identical bits
 
+
+
+# ---------------------------------------------------------------------------------------------------------
+# GP smoother of the data generators
+# ---------------------------------------------------------------------------------------------------------
+def test_golden_gp_smoother(golden):
+    from data_utils import smoothing
+    g = golden("smoothing")
+    for name in ("dosc", "lv"):
+        sig = float(g[name + "_sigma_in"])
+        dX, X = smoothing.num_diff_gp(g[name + "_x"], float(g[name + "_dt"]), float(g[name + "_noise"]),
+                                      g[name + "_std"], None if np.isnan(sig) else sig)
+        assert X.dtype == np.float64 and X.shape == g[name + "_X"].shape
+        assert rel(X, g[name + "_X"]) < 1e-9, rel(X, g[name + "_X"])
+        assert rel(dX, g[name + "_dX"]) < 1e-6, rel(dX, g[name + "_dX"])
