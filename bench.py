@@ -195,7 +195,7 @@ def main():
 
     import torch.distributed as dist
     from sindy_b200 import native
-    from sindy_b200.dist import FitStepper, HostStreamedStep, ShardedTrainStep, mse_from_sums
+    from sindy_b200.dist import FitStepper, HostStreamedStep, ShardedTrainStep, bind_to_gpu_numa_node, mse_from_sums
 
     native.load()  # fails loudly if the CUDA library is missing: there is no fallback path
     torch.cuda.set_device(local_rank)
@@ -338,6 +338,7 @@ def main():
     kern_ms = float(kt)
 
     # ---- e2e: host buffers, H2D inside the timed region, loss read back ----
+    numa_node = bind_to_gpu_numa_node(dev) if world > 1 else None   # node-local pinned buffers (one process per GPU)
     host_step = HostStreamedStep(lib, chunk_samples=1 << 22, device=dev, flags=flags)
     xh = torch.empty(n_local, D, dtype=torch.float32, pin_memory=True)
     dxh = torch.empty(n_local, D, dtype=torch.float32, pin_memory=True)
@@ -435,7 +436,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": 8,
                 "steps": args.e2e_steps,
                 "how": "HostStreamedStep: pinned host x/dx -> 2 staging buffers on 2 streams -> fused kernel per "
-                       "chunk; loss read back with .item()"},
+                       "chunk; loss read back with .item()", "numa_node": numa_node},
         "roofline": roofline, "roofline_hbm": roofline_hbm,
     }
 

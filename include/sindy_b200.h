@@ -15,6 +15,9 @@
  *  - the caller owns all buffers, including workspaces (`sb_workspace_bytes`); nothing is retained
  *    after the call returns except per-device constant tables;
  *  - return value: 0 = ok, negative = `sb_status`; `sb_last_error()` gives a thread-local message;
+ *  - re-entrant from several host threads; ONE restriction: the specialised kernels read the coefficient matrix from a
+ *    single per-device constant-bank slot, so two calls that take DIFFERENT coefficients (w / xi) must not be in flight
+ *    on different streams of the same device at the same time (same coefficients, e.g. chunks of one step: fine);
  *  - no C++ exception crosses the ABI; there is NO CPU fallback: without a CUDA device every
  *    compute entry point returns SB_ERR_CUDA.
  *
@@ -234,7 +237,8 @@ int sb_wsindy_integrals(const float* x, int64_t n_traj, int64_t T, const sb_libr
 void sb_debug_trace(void* dev_buf);
 
 /* FP32 FMA-pipe peak microbenchmark used for the roofline denominator (not in MEASURED_PEAKS.json):
- * variant 0 = scalar FFMA, 1 = packed FFMA2 (fma.rn.f32x2), 2 = FFMA2 with a constant-bank operand.
+ * variant 0 = scalar FFMA, 1 = packed FFMA2 (fma.rn.f32x2), 2 = FFMA2 with a constant-bank operand; design probes in the
+ * same unit (2 x lane-operations/s): 3 = warp shuffles only, 4 = variant 2 with one SHFL per 4 FFMA2 (FFMA2 counted).
  * Runs on `stream`, writes the achieved TFLOP/s (2 flop per lane-FMA) to *tflops_host. Synchronises. */
 int sb_fp32_peak(int variant, int iters, double* tflops_host, void* stream);
 

@@ -390,7 +390,7 @@ void sb_debug_trace(void* dev_buf) { fused_set_trace(reinterpret_cast<unsigned l
 
 int sb_fp32_peak(int variant, int iters, double* tflops_host, void* stream) {
   SB_TRY(check_ptr(tflops_host, "tflops_host"));
-  if (variant < 0 || variant > 2 || iters < 1) { set_error("bad variant/iters"); return SB_ERR_INVALID; }
+  if (variant < 0 || variant > 4 || iters < 1) { set_error("bad variant/iters"); return SB_ERR_INVALID; }
   return fp32_peak(variant, iters, tflops_host, (cudaStream_t)stream);
 }
 

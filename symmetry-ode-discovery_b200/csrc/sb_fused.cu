@@ -18,6 +18,9 @@
 // assignment, per-CTA partials in fp64 and an ordered last-block reduction => deterministic results.
 #include <cstdlib>
 
+#include <atomic>
+#include <mutex>
+
 #include "sb_common.cuh"
 #include "sb_tma.cuh"
 
@@ -615,8 +618,11 @@ __global__ void pack_w_kernel(const float* __restrict__ xi, const float* __restr
 }
 
 // ---- host side ------------------------------------------------------------------------------------
+std::mutex g_init_mutex;   // guards the lazily built per-device tables below (the library is re-entrant)
+
 int tuning_variant() {
-  static int v = -1;
+  static std::atomic<int> cached{-1};
+  int v = cached.load(std::memory_order_acquire);
   if (v < 0) {
     const char* e = getenv("SB_FUSED_VARIANT");
     // A/B on B200 at N = 1e8 (one launch, median of 15): 15: 1.335 ms, 11: 1.365, 47: 1.387, 143: 1.378; at the 8-GPU
@@ -626,6 +632,7 @@ int tuning_variant() {
     // 1.342 — a scalar FMUL holds the FMA pipe one cycle, a packed one two, so packing only saves issue slots.
     v = e ? atoi(e) : 15;
     if (v < 0 || v > 511) v = 15;
+    cached.store(v, std::memory_order_release);
   }
   return v;
 }
@@ -638,6 +645,7 @@ int launch_fused_var(FusedArgs a, void* ws, int64_t ws_bytes, cudaStream_t s) {
   int dev = 0;
   SB_CUDA_TRY(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64) { set_error("device index %d out of range", dev); return SB_ERR_INVALID; }
+  std::unique_lock<std::mutex> lock(g_init_mutex);
   if (grid_cached[dev] == 0) {
     SB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes));
     int per_sm = 0, sms = 0;
@@ -648,11 +656,13 @@ int launch_fused_var(FusedArgs a, void* ws, int64_t ws_bytes, cudaStream_t s) {
     if (g > kMaxPartialBlocks) g = kMaxPartialBlocks;
     grid_cached[dev] = g;
   }
+  const int grid_max = grid_cached[dev];
+  lock.unlock();
   a.n_bulk = a.n & ~(int64_t)3;
   a.n_tiles = (a.n_bulk + C::kTile - 1) / C::kTile;
   // one contiguous, equally sized range per CTA; no more CTAs than half-tiles of work
   int64_t grid = (a.n_bulk + C::kTile / 2 - 1) / (C::kTile / 2);
-  if (grid > grid_cached[dev]) grid = grid_cached[dev];
+  if (grid > grid_max) grid = grid_max;
   // the last block stages all partial rows (+ kWarps sub-sum rows of doubles) in the tile ring
   constexpr int64_t kRowsFit = ((int64_t)C::kSmemData - 128 - (int64_t)C::kWarps * C::kRow * 8) / (C::kRow * 4);
   if (grid > kRowsFit) grid = kRowsFit;
@@ -691,6 +701,7 @@ int const_slot(float** out) {
   int dev = 0;
   SB_CUDA_TRY(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64) { set_error("device index %d out of range", dev); return SB_ERR_INVALID; }
+  std::lock_guard<std::mutex> lock(g_init_mutex);
   if (!base[dev]) {
     void* p = nullptr;
     SB_CUDA_TRY(cudaGetSymbolAddress(&p, c_w2));

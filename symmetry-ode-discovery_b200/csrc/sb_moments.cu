@@ -13,6 +13,9 @@
 // warps 0-3 own a ∈ [0,2), warps 4-7 a ∈ [2,10] (one warp of each per scheduler), both sweep the same TMA-staged x tile (x is read once, 4·d
 // bytes per sample). fp32 per thread, fp64 across threads, ordered last-block reduction (deterministic). A tiny
 // gather kernel then writes the K×K Gram from the moments.
+#include <atomic>
+#include <mutex>
+
 #include "sb_common.cuh"
 #include "sb_tma.cuh"
 
@@ -280,6 +283,8 @@ int run_moments(const float* x, int64_t n, const LibTab& t, double* gram_out, do
   int dev = 0;
   SB_CUDA_TRY(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64) { set_error("device index %d out of range", dev); return SB_ERR_INVALID; }
+  static std::mutex init_mutex;   // the lazily built per-device launch geometry (the library is re-entrant)
+  std::unique_lock<std::mutex> lock(init_mutex);
   if (grid_cached[dev] == 0) {
     SB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes));
     int per_sm = 0, sms = 0;
@@ -290,11 +295,13 @@ int run_moments(const float* x, int64_t n, const LibTab& t, double* gram_out, do
     if (g > kMaxPartialBlocks) g = kMaxPartialBlocks;
     grid_cached[dev] = g;
   }
+  const int grid_max = grid_cached[dev];
+  lock.unlock();
   MomArgs a{};
   a.x = x; a.n = n;
   a.n_bulk = n & ~(int64_t)3;
   a.n_tiles = (a.n_bulk + kTile - 1) / kTile;
-  int64_t grid = a.n_tiles < grid_cached[dev] ? a.n_tiles : grid_cached[dev];
+  int64_t grid = a.n_tiles < grid_max ? a.n_tiles : grid_max;
   if (grid < 1) grid = 1;
   const int64_t need = kWsHeaderBytes + (grid + 1) * C::NM * (int64_t)sizeof(double);
   if (ws_bytes < need) {

@@ -4,6 +4,9 @@
 //   0: scalar FFMA            acc = a * m[j] + acc
 //   1: packed FFMA2           acc2 = a2 * m2[j] + acc2        (fma.rn.f32x2)
 //   2: packed FFMA2, constant acc2 = c2[j] * m2[j] + acc2     (the pattern of the prediction step)
+// Design probes (not roofline denominators; reported in the same unit, 2 x lane-operations per second):
+//   3: warp shuffles only     m[j].x = shfl_xor(m[j].x, 1)    (32 lane-operations per SHFL)
+//   4: pattern 2 with one SHFL after every 4 FFMA2 (only the FFMA2 are counted): do shuffles cost FMA issue slots?
 #include "sb_common.cuh"
 
 namespace sb {
@@ -36,6 +39,12 @@ __global__ void __launch_bounds__(kThreads) peak_kernel(const float* __restrict_
           acc[j].y = fmaf(a.y, m[j].y, acc[j].y);
         } else if (VARIANT == 1) {
           acc[j] = __ffma2_rn(a, m[j], acc[j]);
+        } else if (VARIANT == 3) {
+          m[j].x = __shfl_xor_sync(0xffffffffu, m[j].x, 1);
+          m[j].y = __shfl_xor_sync(0xffffffffu, m[j].y, 2);
+        } else if (VARIANT == 4) {
+          acc[j] = __ffma2_rn(c_peak[j], m[j], acc[j]);
+          if (j % 4 == 3) m[(j + 8) % kChains].x = __shfl_xor_sync(0xffffffffu, m[(j + 8) % kChains].x, 1);
         } else {
           acc[j] = __ffma2_rn(c_peak[j], m[j], acc[j]);
         }
@@ -44,7 +53,7 @@ __global__ void __launch_bounds__(kThreads) peak_kernel(const float* __restrict_
   }
   float s = 0.f;
 #pragma unroll
-  for (int j = 0; j < kChains; ++j) s += acc[j].x + acc[j].y;
+  for (int j = 0; j < kChains; ++j) s += acc[j].x + acc[j].y + m[j].x + m[j].y;
   out[tid] = s;
 }
 
@@ -70,6 +79,8 @@ int fp32_peak(int variant, int iters, double* tflops_host, cudaStream_t s) {
   auto launch = [&](int it) {
     if (variant == 0) peak_kernel<0><<<blocks, kThreads, 0, s>>>(in, out, it);
     else if (variant == 1) peak_kernel<1><<<blocks, kThreads, 0, s>>>(in, out, it);
+    else if (variant == 3) peak_kernel<3><<<blocks, kThreads, 0, s>>>(in, out, it);
+    else if (variant == 4) peak_kernel<4><<<blocks, kThreads, 0, s>>>(in, out, it);
     else peak_kernel<2><<<blocks, kThreads, 0, s>>>(in, out, it);
   };
   launch(iters / 8 + 1);  // warm-up

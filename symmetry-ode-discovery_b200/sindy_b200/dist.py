@@ -25,6 +25,37 @@ from . import native
 from .native import Library
 
 
+def bind_to_gpu_numa_node(device) -> Optional[int]:
+    """Pin this process to the CPUs of the NUMA node the GPU hangs off (sysfs: the PCI device's `numa_node` and the
+    node's `cpulist`), so that pinned host buffers allocated afterwards are node-local: with one process per GPU on a
+    two-socket box, host->device streams otherwise cross the socket interconnect. Returns the node, or None if the
+    topology is not exposed (then nothing is changed)."""
+    try:
+        p = torch.cuda.get_device_properties(device)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+    except Exception:   # no CUDA device / properties without PCI ids
+        return None
+    try:
+        path = f"/sys/bus/pci/devices/{bdf.lower()}/numa_node"
+        with open(path) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except (OSError, ValueError):
+        return None
+
+
 def _world(group) -> int:
     return dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
 

@@ -226,3 +226,29 @@ def test_lie_regulariser_quadratic_form_equals_gram_form():
         assert torch.equal(H, H.T)
         assert abs(float(w @ H @ w) - float(loss.detach())) <= 1e-12 * float(loss.detach())
         assert float((2 * H @ w - W.grad.reshape(-1)).abs().max()) <= 1e-12 * float(W.grad.abs().max())
+
+
+def test_fit_step_argument_validation_without_a_device():
+    """sb_fit_step / sb_load_w reject bad arguments with a status and a message before touching CUDA."""
+    from sindy_b200 import native
+    lib = native.load()
+    L = native._CLibrary(3, 5, 0, 0)
+    opt = native._CFitOptions(native.SB_OPT_ADAM, 1e-3, 0.9, 0.999, 1e-8, 1.0, 0.0, 0.0, None)
+    one = ctypes.c_void_p(16)   # a non-NULL, 16-byte aligned dummy address: validation never dereferences it
+
+    def call(x=one, dx=one, n=8, xi=one, o=ctypes.byref(opt), state=one, packed=one, ws=one, world=1, flags=0):
+        return lib.sb_fit_step(x, dx, n, ctypes.byref(L), xi, None, o, state, packed, one, one, ws, 1 << 20, None, world,
+                               0, None, flags, None)
+
+    assert call(x=None) == -1 and b"x is NULL" in lib.sb_last_error()
+    assert call(o=None) == -1 and b"opt" in lib.sb_last_error()
+    assert call(state=None) == -1 and b"opt_state" in lib.sb_last_error()
+    assert call(flags=2) == -1 and b"call_flags" in lib.sb_last_error()
+    assert call(n=-1) == -1
+    assert call(world=2) == -1 and b"peer_bufs" in lib.sb_last_error()
+    bad = native._CFitOptions(7, 1e-3, 0.9, 0.999, 1e-8, 1.0, 0.0, 0.0, None)
+    assert call(o=ctypes.byref(bad)) == -1 and b"optimiser" in lib.sb_last_error()
+    assert call(x=ctypes.c_void_p(20)) == -2 and b"aligned" in lib.sb_last_error()       # misaligned input
+    Lg = native._CLibrary(2, 2, 0, 1)                                                    # exp column: no fused kernel
+    assert lib.sb_load_w(ctypes.byref(Lg), one, None, None) == -2
+    assert lib.sb_load_w(ctypes.byref(L), None, None, None) == -1
