@@ -374,6 +374,22 @@ def gen_adam():
     finally:
         os.chdir(cwd)
     out.update({"x": x, "dx": dx, "final_Xi": reg.Xi.detach(), "final_mask": reg.mask})
+    # the same loop with w_sym_reg = 0 (the regulariser is still evaluated and logged by the reference but does not
+    # move the parameters): pins the one-launch fused iteration of train.train_SIGED
+    reg0 = make_reg(2, 2, False, False, seed=5)
+    reg0.Xi.data = out["init_Xi"].clone()
+    os.chdir("/tmp")
+    try:
+        ref_train.train_SIGED(
+            train_loader=loader, test_loader=loader, num_epochs=9, device="cpu", log_interval=1000,
+            save_interval=100000, save_dir="golden_tmp", autoencoder=ae, discriminator=torch.nn.Identity(), generator=gen,
+            lr_ae=1e-3, lr_d=1e-3, lr_g=1e-3, w_recon=0.0, w_gan=0.0, w_reg_norm=0.0, w_reg_ortho=0.0,
+            w_reg_closure=0.0, use_original_x=False, gan_st_freq=5, gan_st_thres=0.3, ae_arch='mlp', regressor=reg0,
+            use_latent=False, lr_sindy=2e-2, w_sindy_z=0.0, w_sindy_x=0.8, sindy_reg_type='l1', w_sindy_reg=1e-3,
+            w_sym_reg=0.0, st_freq=3, threshold=0.02, int_t=0.1, int_dt=0.01, print_eq=False, print_li=False)
+    finally:
+        os.chdir(cwd)
+    out.update({"nosym_final_Xi": reg0.Xi.detach(), "nosym_final_mask": reg0.mask})
     save("adam", **out)
 
 

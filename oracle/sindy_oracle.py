@@ -222,7 +222,7 @@ def torch_adam_loop(x, dx, Xi, mask, p, n_steps, lr, w_sindy_x=1.0, w_sindy_reg=
         opt.zero_grad()
         loss.backward()
         opt.step()
-        losses.append(float(loss))
+        losses.append(float(loss.detach()))
     return Xi.detach().clone(), losses, Xi.grad.detach().clone()
 
 

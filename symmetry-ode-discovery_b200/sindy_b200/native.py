@@ -376,6 +376,10 @@ def fit_step(x: torch.Tensor, dx: torch.Tensor, xi: torch.Tensor, mask: Optional
     sym_quad (symreg.quadratic_form) adds w_sym × the linear Lie-derivative regulariser of the data set."""
     xf = _flat(_f32c(x, "x"), lib.dim, "x")
     dxf = _flat(_f32c(dx, "dx"), lib.dim, "dx")
+    if xf.data_ptr() % 16:       # the TMA-staged kernel needs 16-byte aligned inputs (a view at an odd offset)
+        xf = xf.clone()
+    if dxf.data_ptr() % 16:
+        dxf = dxf.clone()
     _require_cuda(xi, "xi")
     if xi.dtype != torch.float32 or not xi.is_contiguous():
         raise ValueError("`xi` is updated in place: it must be a contiguous float32 CUDA tensor")

@@ -203,12 +203,19 @@ def train_SIGED(
     int_t, int_dt, **kwargs
 ):
     """Adam loop of the reference (`train.py:382-614`), equation-discovery part (the GAN/autoencoder updates are
-    commented out there too). Data-space branch: MSE + w_sym_reg·symmreg_i + L1; thresholding every st_freq epochs."""
+    commented out there too). Data-space branch: MSE + w_sym_reg·symmreg_i + L1; thresholding every st_freq epochs.
+    With w_sym_reg == 0 and an unconstrained regressor on a specialised library the loop runs fused, one launch per
+    iteration (`fused_step=False` keeps the operator-by-operator path, which also logs the unweighted sym-reg value)."""
     if sindy_reg_type != 'l1':
         raise ValueError(f'Unknown regularization type: {sindy_reg_type}')
     if use_latent:
         raise NotImplementedError('train_SIGED(use_latent=True): the latent Adam branch of the reference raises '
                                   'TypeError as shipped (train.py:505); use train_SIGED_lbfgs')
+    if kwargs.get('fused_step', True) and w_sym_reg == 0.0 and _fusable(regressor):
+        # the regulariser has weight 0: it cannot move the parameters (the reference still evaluates it for its log
+        # line). Every batch iteration — forward, MSE + L1, backward, Adam update — is ONE kernel launch (sb_fit_step).
+        return _train_adam_fused(train_loader, num_epochs, device, log_interval, save_interval, save_dir, regressor,
+                                 lr_sindy, w_sindy_x, w_sindy_reg, st_freq, threshold, kwargs.get('print_eq'))
     optimizer = torch.optim.Adam(regressor.parameters(), lr=lr_sindy)
     symm_loss = make_symmreg_pttrain(autoencoder, generator)
     for epoch in range(num_epochs):
@@ -237,6 +244,57 @@ def train_SIGED(
             print(', '.join([f'Epoch {epoch}'] + [f'{k}: {v:.4f}' for k, v in metrics.items()]))
             if kwargs.get('print_eq'):
                 regressor.print()
+        _log(metrics)
+        if (epoch + 1) % save_interval == 0:
+            _save(regressor, save_dir, f'regressor_{epoch}.pt')
+
+
+def _fusable(regressor):
+    """Unconstrained regressor on a CUDA device whose library has a specialised fused kernel."""
+    from sindy_b200 import native
+    if getattr(regressor, 'constraint', False) or not isinstance(getattr(regressor, 'Xi', None), torch.nn.Parameter):
+        return False
+    if not regressor.Xi.is_cuda:
+        return False
+    return native.train_step_variant(regressor.library).startswith('fused')
+
+
+def _train_adam_fused(train_loader, num_epochs, device, log_interval, save_interval, save_dir, regressor, lr_sindy,
+                      w_sindy_x, w_sindy_reg, st_freq, threshold, print_eq):
+    """Adam loop of `train.py:491-540` (data-space branch, w_sym_reg = 0) with one launch per iteration. The kernel
+    updates `regressor.Xi` in place with torch's Adam arithmetic and leaves Ξ⊙mask in the constant bank for the next
+    batch; anything else that may load coefficients (thresholding, printing) clears that promise."""
+    from sindy_b200 import native
+    lib = regressor.library
+    xi = regressor.Xi.data
+    if xi.dtype != torch.float32 or not xi.is_contiguous():
+        raise ValueError('regressor.Xi must be a contiguous float32 parameter')
+    state = native.fit_state(lib, xi.device)
+    resident = False
+    for epoch in range(num_epochs):
+        mse_terms, loss_terms = [], []
+        regressor.train()
+        for x, dx in train_loader:
+            x, dx = x.to(device), dx.to(device)
+            n = x.reshape(-1, lib.dim).shape[0]
+            loss, _, packed = native.fit_step(x, dx, xi, regressor.mask, lib, 'adam', lr_sindy, w_mse=w_sindy_x,
+                                              w_l1=w_sindy_reg, state=state, w_resident=resident)
+            resident = True
+            mse_terms.append(packed[0] / (n * lib.dim))     # device scalars: no host sync inside the epoch
+            loss_terms.append(loss.clone())
+        if st_freq > 0 and (epoch + 1) % st_freq == 0:
+            regressor.set_threshold(threshold)
+            resident = False
+        mse = torch.stack(mse_terms).double()
+        tot = torch.stack(loss_terms).double()
+        metrics = {'loss_sindy_x': float(mse.mean())}
+        if w_sindy_reg != 0.0:
+            metrics['loss_sindy_reg'] = float(((tot - w_sindy_x * mse) / w_sindy_reg).mean())
+        if (epoch + 1) % log_interval == 0:
+            print(', '.join([f'Epoch {epoch}'] + [f'{k}: {v:.4f}' for k, v in metrics.items()]))
+            if print_eq:
+                regressor.print()
+                resident = False
         _log(metrics)
         if (epoch + 1) % save_interval == 0:
             _save(regressor, save_dir, f'regressor_{epoch}.pt')

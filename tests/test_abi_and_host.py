@@ -252,3 +252,22 @@ def test_fit_step_argument_validation_without_a_device():
     Lg = native._CLibrary(2, 2, 0, 1)                                                    # exp column: no fused kernel
     assert lib.sb_load_w(ctypes.byref(Lg), one, None, None) == -2
     assert lib.sb_load_w(ctypes.byref(L), None, None, None) == -1
+
+
+def test_c_consumer_links_and_validates(tmp_path):
+    """include/sindy_b200.h is a C header and libsindy_b200.so a C-ABI library: a gcc-compiled C program links it,
+    queries the library tables and gets status codes (no C++ exception, no crash) for bad arguments — no GPU needed."""
+    import shutil
+    import subprocess
+    from sindy_b200 import native
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    native.load()
+    exe = str(tmp_path / "abi_smoke")
+    libdir = os.path.dirname(native.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "c", "abi_smoke.c"), "-o", exe, "-L", libdir, "-lsindy_b200",
+                    f"-Wl,-rpath,{libdir}"], check=True)
+    res = subprocess.run([exe], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "c abi ok" in res.stdout

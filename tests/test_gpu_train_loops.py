@@ -195,3 +195,34 @@ def test_fit_step_with_lie_regulariser_in_the_epilogue(d, p, monkeypatch):
     losses = [float(st.step()) for _ in range(8)]
     np.testing.assert_allclose(losses, ref_losses, rtol=5e-5)
     assert rel(st.xi, reg.Xi) < 1e-4, rel(st.xi, reg.Xi)
+
+
+def test_golden_adam_loop_without_symreg_runs_fused(golden, monkeypatch):
+    """train_SIGED with w_sym_reg = 0 takes the one-launch-per-iteration path (sb_fit_step) and lands on the
+    reference's parameters and mask (golden run of the unmodified reference: 9 epochs x 4 batches, thresholding every 3)."""
+    import sindy
+    import train
+    from sindy_b200 import native
+    g = golden("adam")
+    x, dx = dev(g["x"]), dev(g["dx"])
+    loader = [(x[i:i + 128], dx[i:i + 128]) for i in range(0, x.shape[0], 128)]
+    calls = {"fit": 0}
+    real = native.fit_step
+
+    def counting(*a, **k):
+        calls["fit"] += 1
+        return real(*a, **k)
+
+    monkeypatch.setattr(native, "fit_step", counting)
+    reg = sindy.SINDyRegression(2, 2, False, False, threshold=0.02, device="cuda", constrain_constant=True)
+    reg.Xi.data = dev(g["init_Xi"])
+    train.train_SIGED(
+        train_loader=loader, test_loader=loader, num_epochs=9, device="cuda", log_interval=3, save_interval=100000,
+        save_dir=None, autoencoder=torch.nn.Identity(), discriminator=torch.nn.Identity(), generator=torch.nn.Identity(),
+        lr_ae=1e-3, lr_d=1e-3, lr_g=1e-3, w_recon=0.0, w_gan=0.0, w_reg_norm=0.0, w_reg_ortho=0.0, w_reg_closure=0.0,
+        use_original_x=False, gan_st_freq=5, gan_st_thres=0.3, ae_arch='mlp', regressor=reg, use_latent=False,
+        lr_sindy=2e-2, w_sindy_z=0.0, w_sindy_x=0.8, sindy_reg_type='l1', w_sindy_reg=1e-3, w_sym_reg=0.0, st_freq=3,
+        threshold=0.02, int_t=0.1, int_dt=0.01, print_eq=True, print_li=False)
+    assert calls["fit"] == 36
+    assert np.array_equal(reg.mask.cpu().numpy(), g["nosym_final_mask"])
+    assert rel(reg.Xi, g["nosym_final_Xi"]) < 1e-4, rel(reg.Xi, g["nosym_final_Xi"])
