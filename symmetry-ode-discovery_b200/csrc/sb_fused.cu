@@ -487,8 +487,8 @@ fused_step_kernel(FusedArgs a) {
       }
       fin[tid] = v;
     }
-    if (tid == 0) *a.peer.epoch = epoch;
     __syncthreads();
+    if (tid == 0) *a.peer.epoch = epoch;   // after the barrier: every thread has read the old value long ago
   }
   const double n_total = fin[C::NV];
   stamp(a.trace, 5);

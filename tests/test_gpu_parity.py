@@ -140,6 +140,57 @@ def test_train_step_linearity_large(nat):
     assert abs(float(g1["sum_sq"]) - float(quad)) < 2e-5 * float(quad)
 
 
+def test_full_size_properties_1e8_samples_and_1e6_ics(nat):
+    """BASELINE.json's full sizes (configs[4]: 1e8 samples, d = 3, degree 5; 1e6 ICs x 2000 RK4 steps), where the oracle
+    cannot go: size-independent properties. Sums are additive over any split of the samples (contiguous per-CTA
+    ranges, ragged tails), the residual sum obeys the quadratic identity with the power-sum Gram, the one-launch
+    iteration is bitwise reproducible, and the rollout is a semigroup (2000 steps == 1000 + 1000, bitwise)."""
+    lib = nat.Library(3, 5)
+    n = 100_000_000
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.rand(n, 3, device="cuda", generator=gen) * 2 - 1
+    dx = torch.randn(n, 3, device="cuda", generator=gen)
+    W = torch.randn(3, 56, device="cuda", generator=gen)
+    f = nat.SB_STEP_LOSS | nat.SB_STEP_GRAD
+    full = nat.train_step(x, dx, W, lib, f).clone()
+    assert float(full[1]) == n
+    cut = 37_000_004      # multiple of 4: the second part stays 16-byte aligned for the TMA path
+    parts = nat.train_step(x[:cut], dx[:cut], W, lib, f).clone() + nat.train_step(x[cut:], dx[cut:], W, lib, f)
+    assert rel(parts, full) < 1e-6, rel(parts, full)
+    ragged = nat.train_step(x[:n - 3], dx[:n - 3], W, lib, f).clone() + nat.train_step(x[n - 3:], dx[n - 3:], W, lib, f)
+    assert float(ragged[1]) == n and rel(ragged, full) < 1e-6
+    fb = nat.SB_STEP_GRAM | nat.SB_STEP_B
+    assert nat.train_step_variant(lib, nat.SB_STEP_GRAM) == "moments"
+    gb = nat.unpack_step(nat.train_step(x, dx, None, lib, fb), lib, fb)
+    sum_dx2 = sum(float((dx[i:i + 10_000_000].double() ** 2).sum()) for i in range(0, n, 10_000_000))
+    Wd = W.double()
+    quad = float(torch.einsum('ik,kl,il->', Wd, gb["gram"], Wd) - 2 * (Wd * gb["b"].T).sum()) + sum_dx2
+    assert abs(float(full[0]) - quad) < 2e-5 * quad
+    assert rel(full[2:].view(3, 56), Wd @ gb["gram"] - gb["b"].T) < 5e-5
+    # one-launch Adam iteration at full size: bitwise reproducible, loss consistent with the sums
+    runs = []
+    for _ in range(2):
+        xi = W.clone()
+        state = nat.fit_state(lib, xi.device)
+        loss, grad, packed = nat.fit_step(x, dx, xi, None, lib, "adam", 1e-3, state=state)
+        runs.append((float(loss), grad.clone(), xi.clone(), packed.clone()))
+    assert runs[0][0] == runs[1][0] and torch.equal(runs[0][1], runs[1][1]) and torch.equal(runs[0][2], runs[1][2])
+    assert torch.equal(runs[0][3], full)
+    assert abs(runs[0][0] - float(full[0]) / (3 * n)) < 1e-6 * runs[0][0]
+    del x, dx
+    # 1e6 initial conditions, dt = 0.002 (ode.py:7 defaults), every 10th state stored
+    Xi = torch.zeros(3, 56, device="cuda")
+    Xi[0, 1], Xi[0, 2], Xi[1, 1], Xi[1, 2], Xi[1, 6], Xi[2, 5], Xi[2, 3] = -10.0, 10.0, 2.8, -1.0, -1.0, 1.0, -8.0 / 3.0
+    x0 = torch.rand(1_000_000, 3, device="cuda", generator=gen) * 2 - 1
+    traj, _, last = nat.rollout(x0, Xi, lib, 0.002, 2000, 10, "rk4")
+    assert traj.shape == (200, 1_000_000, 3) and torch.equal(traj[-1], last)
+    _, _, mid = nat.rollout(x0, Xi, lib, 0.002, 1000, 10, "rk4", want_traj=False)
+    assert torch.equal(mid, traj[99])
+    _, _, end = nat.rollout(mid, Xi, lib, 0.002, 1000, 10, "rk4", want_traj=False)
+    assert torch.equal(end, last)
+    assert bool(torch.isfinite(last).all())
+
+
 # ---------------------------------------------------------------------------------------------------------
 # derivatives: backward, jvp, jvp-backward; autograd closure incl. the double-vjp trick
 # ---------------------------------------------------------------------------------------------------------
