@@ -2,7 +2,9 @@
 //
 // Replaces, in ONE pass over (x, dx), the reference's `regressor(x)` (Θ materialised column by column,
 // `sindy.py:79-82`), `MSELoss` (`train.py:663-664`) and the Θ-side of `loss.backward()` (`train.py:689`):
-//   r = Θ(x)·Wᵀ − dx,   out = { Σ r², Σ_n r_i Θ_k }   [+ loss and dL/dΞ when the closure epilogue is requested].
+//   r = Θ(x)·Wᵀ − dx,   out = { Σ r², Σ_n r_i Θ_k }   [+ loss and dL/dΞ when the closure epilogue is requested,
+//   + the optimiser update of `train.py:530` and the next launch's coefficients for sb_fit_step: a whole training
+//   iteration is then this one kernel, across GPUs too (all-reduce over NVLink peer memory inside the last block)].
 // Θ never exists in memory: each thread expands the K monomials of its sample in registers by the
 // parent*variable recurrence, forms the d predictions, and accumulates the d×K outer product r ⊗ Θ into
 // private fp32 accumulators. All d·K FMAs of the prediction and of the gradient are issued as packed
@@ -14,8 +16,9 @@
 // (cp.async.bulk ... mbarrier::complete_tx, SASS UBLKCP) into a kStages-deep ring. A "full" mbarrier per stage
 // carries the transaction bytes; an "empty" mbarrier per stage counts one arrival per warp, so the elected
 // producer thread refills a stage without any CTA-wide barrier in the steady state. X and dX are read exactly
-// once, 8·d bytes per sample. Grid = resident CTAs (multiple of the SM count), static round-robin tile
-// assignment, per-CTA partials in fp64 and an ordered last-block reduction => deterministic results.
+// once, 8·d bytes per sample. Grid = resident CTAs (multiple of the SM count), one contiguous sample range per CTA
+// (equal to within 4 samples), one fp32 partial row per CTA, and an ordered, error-free (TwoSum) reduction of the rows
+// by the last block, which stages them in the idle tile ring with TMA => deterministic, fp64-equivalent sums.
 #include <cstdlib>
 
 #include <atomic>
