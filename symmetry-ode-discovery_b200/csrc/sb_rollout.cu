@@ -15,6 +15,8 @@
 // per-call-site offset defeats the hoisting: 52 registers, 9 blocks per SM) costs one indexed LDCU.64 per packed FMA
 // and was measured SLOWER (73.1 ms against 67.9 for 1e6 ICs x 2000 steps): issue-bound. Inline `ld.const` with
 // immediate addresses is hoisted by ptxas just the same.
+#include <cstdlib>
+
 #include "sb_common.cuh"
 
 namespace sb {
@@ -107,6 +109,7 @@ struct RollArgs {
   int64_t stride;
   int method;
   int record_dx;
+  long long opaque;   // always 0, unknown to the compiler: see eval_multi
   void* x_out;
   void* dx_out;
   void* x_last;
@@ -224,7 +227,117 @@ __global__ void __launch_bounds__(kThreads) rollout_gen_kernel(LibTab t, const T
   rollout_body<GenRhs<T, KMAX>, T>(rhs, a);
 }
 
+// ---- fp32 RK4 (odeint layout), NB initial conditions per thread --------------------------------------------------
+// The coefficient pairs are loop-invariant, so ptxas either keeps all of them in vector registers (the kernel above:
+// 164 registers, packed FMAs with three vector operands) or — when an opaque offset `off` (always 0, different per
+// call site) defeats the hoisting — reloads every pair with one indexed LDCU.64 per packed FMA, which is issue-bound
+// with one initial condition per thread. With NB = 2 every loaded pair feeds NB packed FMAs: W stays in the constant
+// bank (uniform-register operands), the thread needs ~100 registers and carries two independent dependency chains.
+// Same operation order per initial condition as rollout_body's odeint branch: bit-identical trajectories.
+template <int D, int P, int NB>
+__device__ __forceinline__ void eval_multi(const float (&x)[NB][D], float (&f)[NB][D], int off) {
+  constexpr int K = Poly<D, P>::K;
+  using L = Poly<D, P>;
+  static_assert(K % 2 == 0, "packed pairs");
+  const float2* w2 = reinterpret_cast<const float2*>(c_rw) + off;
+  float m[NB][K];
+  float2 s0[NB][D], s1[NB][D];
+  static_for<0, NB>([&](auto b) {
+    static_for<0, D>([&](auto i) { s0[b][i] = make_float2(0.f, 0.f); s1[b][i] = make_float2(0.f, 0.f); });
+  });
+  static_for<0, K>([&](auto kc) {
+    constexpr int k = kc;
+    static_for<0, NB>([&](auto bc) {
+      constexpr int b = bc;
+      if constexpr (k == 0) m[b][0] = 1.f;
+      else if constexpr (k <= D) m[b][k] = x[b][k - 1];
+      else {
+        constexpr int pk = L::tab.parent[k];
+        constexpr int vk = L::tab.var[k];
+        m[b][k] = m[b][pk] * x[b][vk];
+      }
+    });
+    if constexpr (k % 2 == 1) {
+      constexpr int kk = k / 2;
+      static_for<0, D>([&](auto ic) {
+        constexpr int i = ic;
+        const float2 w = w2[i * (K / 2) + kk];
+        static_for<0, NB>([&](auto bc) {
+          constexpr int b = bc;
+          const float2 m2 = make_float2(m[b][k - 1], m[b][k]);
+          if constexpr (kk % 2 == 0) s0[b][i] = __ffma2_rn(w, m2, s0[b][i]);
+          else s1[b][i] = __ffma2_rn(w, m2, s1[b][i]);
+        });
+      });
+    }
+  });
+  static_for<0, NB>([&](auto b) {
+    static_for<0, D>([&](auto i) { f[b][i] = (s0[b][i].x + s0[b][i].y) + (s1[b][i].x + s1[b][i].y); });
+  });
+}
+
+template <int D, int P, int NB>
+__global__ void __launch_bounds__(kThreads) rollout_rk4_multi_kernel(RollArgs a) {
+  const int64_t base = (int64_t)blockIdx.x * (kThreads * NB) + threadIdx.x;
+  if (base >= a.n_ics) return;
+  const float* x0 = reinterpret_cast<const float*>(a.x0);
+  float* xo = reinterpret_cast<float*>(a.x_out);
+  float x[NB][D], k1[NB][D], k2[NB][D], k3[NB][D], k4[NB][D], xt[NB][D];
+  bool live[NB];
+  static_for<0, NB>([&](auto bc) {
+    constexpr int b = bc;
+    const int64_t ic = base + (int64_t)b * kThreads;
+    live[b] = ic < a.n_ics;
+    static_for<0, D>([&](auto j) { x[b][j] = live[b] ? x0[ic * D + j] : 0.f; });
+  });
+  const float dt = (float)a.dt, hdt = (float)(a.dt / 2.0), sdt = (float)(a.dt / 6.0), two = 2.f;
+  const int64_t row_elems = a.n_ics * D;
+  int64_t row = 0, until = a.stride;
+  for (int64_t s = 1; s <= a.n_steps; ++s) {
+    eval_multi<D, P, NB>(x, k1, 2 * (int)(s & a.opaque));
+    static_for<0, NB>([&](auto b) { static_for<0, D>([&](auto j) { xt[b][j] = __fadd_rn(x[b][j], __fmul_rn(hdt, k1[b][j])); }); });
+    eval_multi<D, P, NB>(xt, k2, 2 * (int)((s + 1) & a.opaque));
+    static_for<0, NB>([&](auto b) { static_for<0, D>([&](auto j) { xt[b][j] = __fadd_rn(x[b][j], __fmul_rn(hdt, k2[b][j])); }); });
+    eval_multi<D, P, NB>(xt, k3, 2 * (int)((s + 2) & a.opaque));
+    static_for<0, NB>([&](auto b) { static_for<0, D>([&](auto j) { xt[b][j] = __fadd_rn(x[b][j], __fmul_rn(dt, k3[b][j])); }); });
+    eval_multi<D, P, NB>(xt, k4, 2 * (int)((s + 3) & a.opaque));
+    static_for<0, NB>([&](auto b) {
+      static_for<0, D>([&](auto j) {
+        float acc = __fadd_rn(k1[b][j], __fmul_rn(two, k2[b][j]));
+        acc = __fadd_rn(acc, __fmul_rn(two, k3[b][j]));
+        acc = __fadd_rn(acc, k4[b][j]);
+        x[b][j] = __fadd_rn(x[b][j], __fmul_rn(sdt, acc));
+      });
+    });
+    if (--until == 0) {
+      if (xo) {
+        static_for<0, NB>([&](auto bc) {
+          constexpr int b = bc;
+          const int64_t ic = base + (int64_t)b * kThreads;
+          if (live[b]) static_for<0, D>([&](auto j) { xo[row * row_elems + ic * D + j] = x[b][j]; });
+        });
+      }
+      ++row;
+      until = a.stride;
+    }
+  }
+  if (a.x_last) {
+    float* xl = reinterpret_cast<float*>(a.x_last);
+    static_for<0, NB>([&](auto bc) {
+      constexpr int b = bc;
+      const int64_t ic = base + (int64_t)b * kThreads;
+      if (live[b]) static_for<0, D>([&](auto j) { xl[ic * D + j] = x[b][j]; });
+    });
+  }
+}
+
 #define SB_ROLL_SHAPES(X) X(2, 2) X(2, 3) X(3, 2) X(3, 3) X(3, 5)
+
+// SB_ROLLOUT_MULTI=0 selects the one-initial-condition-per-thread kernel for the fp32 RK4 rollout (A/B, bitwise test)
+bool rollout_multi_enabled() {
+  const char* e = getenv("SB_ROLLOUT_MULTI");
+  return !(e && e[0] == '0');
+}
 
 template <class T>
 int launch_rollout(const LibTab& t, const void* w, const RollArgs& a, cudaStream_t s) {
@@ -233,6 +346,14 @@ int launch_rollout(const LibTab& t, const void* w, const RollArgs& a, cudaStream
 #define X(D, P)                                                                                              \
   if (t.d == D && t.n_poly == n_poly_terms(D, P)) {                                                          \
     SB_CUDA_TRY(cudaMemcpyToSymbolAsync(c_rw, w, sizeof(T) * D * Poly<D, P>::K, 0, cudaMemcpyDeviceToDevice, s)); \
+    if constexpr (std::is_same<T, float>::value && Poly<D, P>::K % 2 == 0) {                                   \
+      if (a.method == SB_RK4 && !a.record_dx && rollout_multi_enabled()) {                                     \
+        const unsigned g2 = (unsigned)((a.n_ics + 2 * kThreads - 1) / (2 * kThreads));                         \
+        rollout_rk4_multi_kernel<D, P, 2><<<g2, kThreads, 0, s>>>(a);                                          \
+        SB_LAUNCH_CHECK("rollout_rk4_multi_kernel");                                                           \
+        return SB_OK;                                                                                          \
+      }                                                                                                        \
+    }                                                                                                          \
     rollout_spec_kernel<D, P, T><<<grid, kThreads, 0, s>>>(a);                                                \
     SB_LAUNCH_CHECK("rollout_spec_kernel");                                                                  \
     return SB_OK;                                                                                            \
@@ -254,7 +375,7 @@ int rollout(const void* x0, int64_t n_ics, const LibTab& t, const void* w, doubl
             cudaStream_t s) {
   RollArgs a{};
   a.x0 = x0; a.n_ics = n_ics; a.dt = dt; a.n_steps = n_steps; a.stride = stride; a.method = method;
-  a.record_dx = record_dx; a.x_out = x_out; a.dx_out = dx_out; a.x_last = x_last;
+  a.record_dx = record_dx; a.opaque = 0; a.x_out = x_out; a.dx_out = dx_out; a.x_last = x_last;
   if (dtype == SB_F32) return launch_rollout<float>(t, w, a, s);
   return launch_rollout<double>(t, w, a, s);
 }

@@ -403,6 +403,23 @@ def test_rollout_generic_and_specialised_vs_oracle(nat, d, p, s, e):
 # ---------------------------------------------------------------------------------------------------------
 # a6/a7/a8: symmetry regularisers with frozen stand-ins
 # ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("d,p", [(3, 5), (2, 3), (3, 3), (2, 2)])
+def test_rollout_two_ics_per_thread_is_bitwise_the_single_ic_kernel(nat, d, p, monkeypatch):
+    """The fp32 RK4 rollout integrates two initial conditions per thread (W stays in the constant bank); per initial
+    condition the operation order is that of the one-IC kernel: identical bits, odd batch sizes and ragged tails too."""
+    lib = nat.Library(d, p)
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    W = 0.3 * torch.randn(d, lib.K, device="cuda", generator=gen) * (torch.rand(d, lib.K, device="cuda", generator=gen) > 0.6)
+    for n_ics in (1, 127, 128, 129, 257, 1000):
+        x0 = torch.rand(n_ics, d, device="cuda", generator=gen) - 0.5
+        monkeypatch.setenv("SB_ROLLOUT_MULTI", "1")
+        ta, _, la = nat.rollout(x0, W, lib, 0.01, 37, 5, "rk4")
+        monkeypatch.setenv("SB_ROLLOUT_MULTI", "0")
+        tb, _, lb = nat.rollout(x0, W, lib, 0.01, 37, 5, "rk4")
+        assert ta.shape == (7, n_ics, d)
+        assert torch.equal(ta, tb) and torch.equal(la, lb), n_ics
+
+
 def test_golden_symmreg(nat, golden):
     import sindy
     import model_utils
