@@ -122,36 +122,40 @@ template <class R, int D>
 __device__ __forceinline__ void sweep(const MomArgs& a, const float* tiles, uint64_t* full, uint64_t* empty, int sub,
                                       int nsub, int lane, bool producer, float2 (&acc)[R::NPAIR]) {
   constexpr int kTileFloats = kTile * D;
-  auto tile_count = [&](int64_t tile) -> int {
-    const int64_t rem = a.n_bulk - tile * kTile;
+  // one contiguous sample range per CTA, cut in quads (16-byte aligned TMA sources), equal to within 4 samples; the
+  // first tile travels alone and the rest of the ring follows when it has landed (see sb_fused.cu)
+  const int64_t quads = a.n_bulk >> 2;
+  const int64_t s_begin = 4 * (quads * (int64_t)blockIdx.x / (int64_t)gridDim.x);
+  const int64_t s_end = 4 * (quads * ((int64_t)blockIdx.x + 1) / (int64_t)gridDim.x);
+  const int my_tiles = (int)((s_end - s_begin + kTile - 1) / kTile);
+  auto tile_count = [&](int t) -> int {
+    const int64_t rem = s_end - s_begin - (int64_t)t * kTile;
     return (int)(rem < kTile ? rem : kTile);
   };
-  auto issue = [&](int64_t tile, int stage) {
-    const uint32_t bytes = (uint32_t)tile_count(tile) * D * sizeof(float);
+  auto issue = [&](int t, int stage) {
+    const uint32_t bytes = (uint32_t)tile_count(t) * D * sizeof(float);
     mbar_expect_tx(&full[stage], bytes);
-    tma_load_1d(const_cast<float*>(tiles) + (size_t)stage * kTileFloats, a.x + tile * (int64_t)kTileFloats, bytes,
+    tma_load_1d(const_cast<float*>(tiles) + (size_t)stage * kTileFloats, a.x + (s_begin + (int64_t)t * kTile) * D, bytes,
                 &full[stage]);
   };
-  if (producer) {
-    for (int s = 0; s < kStages; ++s) {
-      const int64_t tile = blockIdx.x + (int64_t)s * gridDim.x;
-      if (tile < a.n_tiles) issue(tile, s);
-    }
-  }
-  int it = 0;
-  for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+  if (producer && my_tiles > 0) issue(0, 0);
+  for (int it = 0; it < my_tiles; ++it) {
     const int stage = it % kStages;
     if (producer && it > 0) {
-      const int64_t next = tile + (int64_t)(kStages - 1) * gridDim.x;
-      if (next < a.n_tiles) {
+      const int next = it + kStages - 1;
+      if (next < my_tiles) {
         const int ps = (it - 1) % kStages;
         mbar_wait(&empty[ps], (uint32_t)((it - 1) / kStages) & 1u);
         issue(next, ps);
       }
     }
     mbar_wait(&full[stage], (uint32_t)(it / kStages) & 1u);
+    if (producer && it == 0) {
+      for (int s = 1; s < kStages; ++s)
+        if (s < my_tiles) issue(s, s);
+    }
     const float* sx = tiles + (size_t)stage * kTileFloats;
-    const int cnt = tile_count(tile);
+    const int cnt = tile_count(it);
 #pragma unroll 1
     for (int j = sub * 32 + lane; j < cnt; j += nsub * 32) {
       float xs[D];
@@ -232,10 +236,17 @@ __global__ void __launch_bounds__(kThreads, 1) moments_kernel(MomArgs a) {
   __syncthreads();
   if (!is_last) return;
   __threadfence();
+  // ordered, with 8 loads in flight per thread (the partials sit in L2: latency-bound) and a fixed association
   for (int e = tid; e < C::NM; e += kThreads) {
-    double v = 0.0;
-    for (unsigned int b = 0; b < gridDim.x; ++b) v += a.partial[(int64_t)b * C::NM + e];
-    a.moments[e] = v;
+    double v[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    for (unsigned int b0 = 0; b0 < gridDim.x; b0 += 8) {
+      double t[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) t[q] = (b0 + q < gridDim.x) ? __ldcg(a.partial + (int64_t)(b0 + q) * C::NM + e) : 0.0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] += t[q];
+    }
+    a.moments[e] = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
   }
   if (tid == 0) *a.ticket = 0u;
 }
@@ -301,7 +312,8 @@ int run_moments(const float* x, int64_t n, const LibTab& t, double* gram_out, do
   a.x = x; a.n = n;
   a.n_bulk = n & ~(int64_t)3;
   a.n_tiles = (a.n_bulk + kTile - 1) / kTile;
-  int64_t grid = a.n_tiles < grid_max ? a.n_tiles : grid_max;
+  int64_t grid = (a.n_bulk + kTile / 2 - 1) / (kTile / 2);
+  if (grid > grid_max) grid = grid_max;
   if (grid < 1) grid = 1;
   const int64_t need = kWsHeaderBytes + (grid + 1) * C::NM * (int64_t)sizeof(double);
   if (ws_bytes < need) {
