@@ -121,7 +121,7 @@ class SINDyRegression(nn.Module):
         flags = native.SB_STEP_GRAM | native.SB_STEP_B
         with torch.no_grad():
             parts = native.unpack_step(native.train_step(x, dx, None, lib, flags), lib, flags)
-            yy = (dx.reshape(-1, lib.dim).double() ** 2).sum()
+            yy = _column_sums_of_squares(dx, lib.dim).sum()
         return {"G": parts["gram"], "b": parts["b"], "yy": yy, "n": float(parts["n"])}
 
     def mse_loss_from_statistics(self, stats):
@@ -249,7 +249,11 @@ def _stlsq_update(regressor, G, b, ridge, n_rows, st_threshold):
     dev = G.device
     H = G + ridge * torch.eye(K, dtype=G.dtype, device=dev)
     mask = regressor.mask > 0.0
-    rcond = float(torch.finfo(torch.float32).eps) * max(n_rows, K)
+    # LAPACK gelsy's default rank tolerance, eps·max(rows, cols) in the reference's fp32 — reproduced so that
+    # rank-deficient fits at the reference's sizes (WSINDy on Sel'kov) drop the same directions. It stops being a rank
+    # test when the row count grows (0.48 at 4e6 rows, 11.9 at 1e8: every direction would be dropped), so it is held at
+    # its value for 2^14 rows (2e-3) beyond that.
+    rcond = float(torch.finfo(torch.float32).eps) * min(max(n_rows, K), 1 << 14)
     prev_mask = regressor.mask.clone()
 
     if bool(torch.all(mask)) and not regressor.constraint:
@@ -290,6 +294,23 @@ def _stlsq_update(regressor, G, b, ridge, n_rows, st_threshold):
     return torch.allclose(prev_mask, regressor.mask)
 
 
+def _column_sums_of_squares(y, d):
+    """Σ_n y[n,i]² per equation as fp64 (d,), in ONE pass without an fp64 copy of y (2.4 GB at N = 1e8)."""
+    return torch.linalg.vector_norm(y.reshape(-1, d), dim=0, dtype=torch.float64) ** 2
+
+
+def stlsq_statistics(regressor, x, y):
+    """The data-dependent part of an STLSQ solve — G = ΘᵀΘ, b = ΘᵀY, Σy² per equation, n — from one pass over (x, y).
+    They do not depend on the mask: `solve_SINDy` forms them once for all its thresholding iterations (the reference
+    rebuilds Θ and re-runs LAPACK on the N-row matrix every iteration, `sindy.py:260-288,319-323`)."""
+    lib = regressor.library
+    flags = native.SB_STEP_GRAM | native.SB_STEP_B
+    with torch.no_grad():
+        parts = native.unpack_step(native.train_step(x, y, None, lib, flags), lib, flags)
+        return {"G": parts["gram"], "b": parts["b"], "yy": _column_sums_of_squares(y, lib.dim),
+                "n": x.reshape(-1, lib.dim).shape[0]}
+
+
 def solve_SINDy_one_step(regressor, x, y, w_sindy_reg, st_threshold, **kwargs):
     '''
     One STLSQ step: argmin_w ||y - Θ(x) w||² + w_sindy_reg²·||w||² on the current support (the reference stacks
@@ -300,16 +321,12 @@ def solve_SINDy_one_step(regressor, x, y, w_sindy_reg, st_threshold, **kwargs):
     driver returns an empty `residuals`, i.e. NaN, for this shape).
     '''
     lib = regressor.library
-    flags = native.SB_STEP_GRAM | native.SB_STEP_B
+    stats = kwargs.get('stats') or stlsq_statistics(regressor, x, y)
     with torch.no_grad():
-        out = native.train_step(x, y, None, lib, flags)
-        parts = native.unpack_step(out, lib, flags)
-        G, b = parts["gram"], parts["b"]
-        n = x.reshape(-1, lib.dim).shape[0]
+        G, b, yy, n = stats["G"], stats["b"], stats["yy"], stats["n"]
         converged = _stlsq_update(regressor, G, b, float(w_sindy_reg) ** 2, n + lib.K, st_threshold)
         # residual of the augmented system with the parameters just written (before masking by the new mask)
         Xi = regressor._current_Xi().to(torch.float64)
-        yy = (y.reshape(-1, lib.dim).double() ** 2).sum(0)
         quad = torch.einsum('ik,kl,il->i', Xi, G, Xi) - 2.0 * torch.einsum('ik,ki->i', Xi, b) + yy
         quad = quad + float(w_sindy_reg) ** 2 * (Xi ** 2).sum(1)
         residual = (quad.mean() / n).to(torch.float32)
@@ -319,8 +336,9 @@ def solve_SINDy_one_step(regressor, x, y, w_sindy_reg, st_threshold, **kwargs):
 def solve_SINDy(regressor, x, y, w_sindy_reg, st_threshold, max_iter=5, **kwargs):
     regressor.reset_mask()
     residual = None
+    stats = stlsq_statistics(regressor, x, y)   # one data pass for all thresholding iterations
     for _ in range(max_iter):
-        residual, converged = solve_SINDy_one_step(regressor, x, y, w_sindy_reg, st_threshold)
+        residual, converged = solve_SINDy_one_step(regressor, x, y, w_sindy_reg, st_threshold, stats=stats)
         if converged:
             break
     return residual
