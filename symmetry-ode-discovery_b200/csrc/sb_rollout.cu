@@ -43,7 +43,9 @@ template <int D, int P, class T>
 struct SpecRhs {
   static constexpr int DN = D;
   __device__ __forceinline__ int dim() const { return D; }
-  __device__ __forceinline__ void eval(const T (&x)[D], T (&f)[D]) const {
+  // `off` (always 0, opaque, different per call site) only matters in fp64: it keeps ptxas from hoisting coefficient
+  // loads out of the time loop into registers it does not have (168 registers + spills -> 136, none)
+  __device__ __forceinline__ void eval(const T (&x)[D], T (&f)[D], int off = 0) const {
     constexpr int K = Poly<D, P>::K;
     T m[K];
     expand_poly<D, P>(x, m);
@@ -63,7 +65,7 @@ struct SpecRhs {
       });
       return;
     }
-    const T* w = reinterpret_cast<const T*>(c_rw);
+    const T* w = reinterpret_cast<const T*>(c_rw) + (std::is_same<T, double>::value ? 2 * off : 0);
     static_for<0, D>([&](auto ic) {
       constexpr int i = ic;
       // two partial sums (even / odd columns) keep the dependent chain short
@@ -85,7 +87,7 @@ struct GenRhs {
   LibTab t;
   const T* w;
   __device__ __forceinline__ int dim() const { return t.d; }
-  __device__ __forceinline__ void eval(const T (&x)[SB_MAX_DIM], T (&f)[SB_MAX_DIM]) const {
+  __device__ __forceinline__ void eval(const T (&x)[SB_MAX_DIM], T (&f)[SB_MAX_DIM], int = 0) const {
     T m[KMAX];
     m[0] = T(1);
     for (int j = 0; j < t.d; ++j) m[1 + j] = x[j];
@@ -141,7 +143,7 @@ __device__ __forceinline__ void rollout_body(const RHS& rhs, const RollArgs& a) 
     const T half = T(0.5), two = T(2), six = T(6);
     int64_t row = 0, until = 0;   // next stored row and steps until it (no 64-bit division in the step loop)
     for (int64_t i = 0; i < a.n_steps; ++i) {
-      rhs.eval(x, k1);
+      rhs.eval(x, k1, (int)(i & a.opaque));
       if (until == 0) {
         if (xo) store(xo, row, x);
         if (dxo) store(dxo, row, k1);
@@ -157,13 +159,13 @@ __device__ __forceinline__ void rollout_body(const RHS& rhs, const RollArgs& a) 
       }
 #pragma unroll
       for (int j = 0; j < DN; ++j) { k1[j] = mul_rn(dt, k1[j]); xt[j] = add_rn(x[j], mul_rn(half, k1[j])); }
-      rhs.eval(xt, k2);
+      rhs.eval(xt, k2, (int)((i + 1) & a.opaque));
 #pragma unroll
       for (int j = 0; j < DN; ++j) { k2[j] = mul_rn(dt, k2[j]); xt[j] = add_rn(x[j], mul_rn(half, k2[j])); }
-      rhs.eval(xt, k3);
+      rhs.eval(xt, k3, (int)((i + 2) & a.opaque));
 #pragma unroll
       for (int j = 0; j < DN; ++j) { k3[j] = mul_rn(dt, k3[j]); xt[j] = add_rn(x[j], k3[j]); }
-      rhs.eval(xt, k4);
+      rhs.eval(xt, k4, (int)((i + 3) & a.opaque));
 #pragma unroll
       for (int j = 0; j < DN; ++j) {
         k4[j] = mul_rn(dt, k4[j]);
@@ -178,20 +180,20 @@ __device__ __forceinline__ void rollout_body(const RHS& rhs, const RollArgs& a) 
     const T hdt = (T)(a.dt / 2.0), sdt = (T)(a.dt / 6.0), two = T(2);
     int64_t row = 0, until = a.stride;   // next stored row and steps until it (no 64-bit division in the step loop)
     for (int64_t s = 1; s <= a.n_steps; ++s) {
-      rhs.eval(x, k1);
+      rhs.eval(x, k1, (int)(s & a.opaque));
       if (a.method == SB_EULER) {
 #pragma unroll
         for (int j = 0; j < DN; ++j) x[j] = add_rn(x[j], mul_rn(dt, k1[j]));
       } else {
 #pragma unroll
         for (int j = 0; j < DN; ++j) xt[j] = add_rn(x[j], mul_rn(hdt, k1[j]));
-        rhs.eval(xt, k2);
+        rhs.eval(xt, k2, (int)((s + 1) & a.opaque));
 #pragma unroll
         for (int j = 0; j < DN; ++j) xt[j] = add_rn(x[j], mul_rn(hdt, k2[j]));
-        rhs.eval(xt, k3);
+        rhs.eval(xt, k3, (int)((s + 2) & a.opaque));
 #pragma unroll
         for (int j = 0; j < DN; ++j) xt[j] = add_rn(x[j], mul_rn(dt, k3[j]));
-        rhs.eval(xt, k4);
+        rhs.eval(xt, k4, (int)((s + 3) & a.opaque));
 #pragma unroll
         for (int j = 0; j < DN; ++j) {
           T acc = add_rn(k1[j], mul_rn(two, k2[j]));
