@@ -152,7 +152,8 @@ int sb_closure(const float* x, const float* dx, int64_t n, const sb_library* lib
  * pointers (peer-mapped, e.g. torch symmetric memory), each at least sb_peer_buffer_bytes(lib, world) bytes and
  * zero-filled before the first call; epoch_dev: a zero-initialised device uint32 owned by this rank. Every rank must
  * make the same sequence of calls. Only the specialised (fused) libraries are supported: SB_ERR_UNSUPPORTED
- * otherwise. packed_out receives the GLOBAL sums. A lost peer makes the kernel give up after ~2 s instead of hanging. */
+ * otherwise. packed_out receives the GLOBAL sums. A lost peer makes the kernel give up after ~2 s instead of hanging;
+ * the sums, loss and gradient of that call are then NaN (never a silently partial result). */
 int sb_closure_peer(const float* x, const float* dx, int64_t n, const sb_library* lib, const float* xi,
                     const float* mask, double w_l1, double* packed_out, float* loss_out, float* grad_out,
                     void* workspace, int64_t workspace_bytes, const void* const* peer_bufs, int world, int rank,

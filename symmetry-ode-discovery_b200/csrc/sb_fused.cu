@@ -486,6 +486,9 @@ fused_step_kernel(FusedArgs a) {
                        : "l"(src)
                        : "memory");
         } while ((q1 != epoch || q3 != epoch) && (clock64() - t0) < 4000000000ll);   // ~2 s: never hang on a lost peer
+        // a peer that never arrived must not pass silently: its contribution poisons the sums, so loss, gradient and
+        // (sb_fit_step) the parameters come out NaN on this rank
+        if (q1 != epoch || q3 != epoch) v = __longlong_as_double(0x7ff8000000000000ll);
         v += __longlong_as_double((long long)(((unsigned long long)q2 << 32) | (unsigned long long)q0));
       }
       fin[tid] = v;
