@@ -271,3 +271,32 @@ def test_c_consumer_links_and_validates(tmp_path):
     res = subprocess.run([exe], capture_output=True, text=True)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "c abi ok" in res.stdout
+
+
+def test_sweep_metrics_follow_eval_eq():
+    """sweep.evaluate / sweep.aggregate restate `evaluation/eval_eq.py:7-85`: correct form = mask equals the truth's
+    support, MSE over the truth's non-zeros, RMSE mean (std) over successful runs and over all runs."""
+    import sweep
+
+    class Reg:
+        constraint = False
+
+        def __init__(self, Xi, mask):
+            self.Xi, self.mask = torch.tensor(Xi, dtype=torch.float32), torch.tensor(mask, dtype=torch.float32)
+
+    truth = np.array([[0.0, -0.1, -1.0, 0.0, 0.0, 0.0], [0.0, 1.0, -0.1, 0.0, 0.0, 0.0]])
+    good = Reg([[0.3, -0.11, -1.02, 0, 0, 0], [0, 0.98, -0.1, 0, 0, 0.5]], [[0, 1, 1, 0, 0, 0], [0, 1, 1, 0, 0, 0]])
+    bad = Reg([[0.0, -0.2, -1.0, 0.4, 0, 0], [0, 1.0, -0.1, 0, 0, 0]], [[0, 1, 1, 1, 0, 0], [0, 1, 1, 0, 0, 0]])
+    rg, rb = sweep.evaluate(good, truth), sweep.evaluate(bad, truth)
+    assert rg["correct_form"].tolist() == [1.0, 1.0] and rg["correct_form_all"]
+    assert rb["correct_form"].tolist() == [0.0, 1.0] and not rb["correct_form_all"]
+    np.testing.assert_allclose(rg["mse"], [((0.01) ** 2 + (0.02) ** 2) / 2, (0.02 ** 2) / 2], rtol=1e-5)
+    np.testing.assert_allclose(rb["mse"], [(0.1 ** 2) / 2, 0.0], atol=1e-9)
+    assert rg["coefficients"][0, 0] == 0.0 and rg["coefficients"][1, 5] == 0.0      # masked entries are reported as 0
+    agg = sweep.aggregate([rg, rb, rg], mse_multiplier=10.0, verbose=False)
+    assert agg["runs"] == 3 and agg["success"].tolist() == [2, 3] and agg["success_all"] == 2
+    r0 = np.sqrt([rg["mse"][0], rb["mse"][0], rg["mse"][0]])
+    np.testing.assert_allclose(agg["rmse"][0], (10 * r0[[0, 2]].mean(), 10 * r0[[0, 2]].std()), rtol=1e-6, atol=1e-12)
+    np.testing.assert_allclose(agg["rmse_any"][0], (10 * r0.mean(), 10 * r0.std()), rtol=1e-6)
+    ra = np.sqrt([rg["mse_all"], rb["mse_all"], rg["mse_all"]])
+    np.testing.assert_allclose(agg["rmse_all_any"], (10 * ra.mean(), 10 * ra.std()), rtol=1e-6)

@@ -226,3 +226,28 @@ def test_golden_adam_loop_without_symreg_runs_fused(golden, monkeypatch):
     assert calls["fit"] == 36
     assert np.array_equal(reg.mask.cpu().numpy(), g["nosym_final_mask"])
     assert rel(reg.Xi, g["nosym_final_Xi"]) < 1e-4, rel(reg.Xi, g["nosym_final_Xi"])
+
+
+def test_seed_sweep_recovers_the_damped_oscillator(capsys):
+    """seeds of an experiment run back to back in one process. Noise-free damped-oscillator data
+    (`damped_oscillator.py:20-33`: 1e4 steps, every 100th kept), degree-2 library, the `dosc/noise20_sindy.cfg` fit
+    settings: every seed recovers dz0 = -0.1 z0 - z1, dz1 = z0 - 0.1 z1 (MSE ~ 1e-9)."""
+    import sindy
+    import sweep
+    from data_utils import ode, systems
+    rng = np.random.default_rng(3)
+    f = systems.dosc()
+    r, th = rng.uniform(0.5, 2.0, 20), rng.uniform(0, 2 * np.pi, 20)
+    x0 = np.stack([r * np.cos(th), r * np.sin(th)], 1)
+    x, dx = ode.solve_ode_batch(f, x0, dt=0.002, num_steps=10000)
+    x, dx = dev(x[::100].reshape(-1, 2)), dev(dx[::100].reshape(-1, 2))
+
+    def make():
+        return sindy.SINDyRegression(2, 2, False, False, threshold=0.05, device="cuda", constrain_constant=True)
+
+    res = sweep.run_seed_sweep(x, dx, f.Xi, range(4), make, subsample=0.5, lr_sindy=0.1, st_freq=50, threshold=0.05,
+                               num_epochs=200)
+    assert [r["seed"] for r in res] == [0, 1, 2, 3]
+    agg = sweep.aggregate(res)
+    assert agg["success_all"] == 4 and agg["rmse_all"][0] < 1e-3
+    assert "Joint success rate = 4/4" in capsys.readouterr().out
