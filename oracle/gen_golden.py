@@ -411,8 +411,40 @@ def gen_smoothing():
     save("smoothing", **out)
 
 
+def gen_api():
+    """The reference's public surface on the hot path as data: parameter names and defaults of the
+    functions / methods the drop-in modules must reproduce. Stored as JSON next to the numeric fixtures."""
+    import inspect
+    import json
+    import train as ref_train
+
+    def sig(fn):
+        out = []
+        for name, p in inspect.signature(fn).parameters.items():
+            d = None if p.default is inspect._empty else repr(p.default)
+            out.append([name, str(p.kind), d])
+        return out
+
+    api = {}
+    for modname, mod in (("sindy", ref_sindy), ("model_utils", ref_mu), ("data_utils.ode", ref_ode), ("train", ref_train)):
+        entry = {}
+        for name, obj in vars(mod).items():
+            if name.startswith("_") or getattr(obj, "__module__", None) != mod.__name__:
+                continue
+            if inspect.isfunction(obj):
+                entry[name] = {"kind": "function", "params": sig(obj)}
+            elif inspect.isclass(obj):
+                methods = {m: sig(f) for m, f in vars(obj).items() if inspect.isfunction(f) and (not m.startswith("_") or m == "__init__")}
+                entry[name] = {"kind": "class", "methods": methods}
+        api[modname] = entry
+    path = os.path.join(OUT, "api_surface.json")
+    with open(path, "w") as f:
+        json.dump(api, f, indent=1, sort_keys=True)
+    print(f"wrote {path} ({os.path.getsize(path) / 1024:.1f} KiB)")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["model", "jvp", "stlsq", "wsindy", "rollout", "symmreg", "lbfgs", "adam", "smoothing"]
+    which = sys.argv[1:] or ["model", "jvp", "stlsq", "wsindy", "rollout", "symmreg", "lbfgs", "adam", "smoothing", "api"]
     for w in which:
         globals()["gen_" + w]()
