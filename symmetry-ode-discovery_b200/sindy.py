@@ -26,7 +26,8 @@ import torch.nn as nn
 from sindy_b200 import native, ops
 from sindy_b200.native import Library
 
-__all__ = ["SINDyRegression", "solve_SINDy_one_step", "solve_SINDy", "WSINDyWrapper"]
+__all__ = ["SINDyRegression", "solve_SINDy_one_step", "solve_SINDy", "WSINDyWrapper", "stlsq_statistics",
+           "allreduce_statistics"]
 
 
 def _poly_index_tuples(dim: int, order: int):
@@ -299,16 +300,36 @@ def _column_sums_of_squares(y, d):
     return torch.linalg.vector_norm(y.reshape(-1, d), dim=0, dtype=torch.float64) ** 2
 
 
-def stlsq_statistics(regressor, x, y):
+def allreduce_statistics(stats, group=None):
+    """Sum the sufficient statistics of sample shards over the ranks of `group` (one all-reduce of K² + K·d + d + 1
+    doubles): afterwards every rank holds the statistics of the WHOLE data set and solves the identical K×K systems,
+    so masks and coefficients stay replicated without further communication. No-op without
+    torch.distributed."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return stats
+    G, b, yy = stats["G"], stats["b"], stats["yy"]
+    flat = torch.cat([G.reshape(-1), b.reshape(-1), yy.reshape(-1),
+                      torch.tensor([float(stats["n"])], dtype=G.dtype, device=G.device)])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    k2, kd = G.numel(), b.numel()
+    return {"G": flat[:k2].view_as(G), "b": flat[k2:k2 + kd].view_as(b), "yy": flat[k2 + kd:k2 + kd + yy.numel()].view_as(yy),
+            "n": int(round(float(flat[-1])))}
+
+
+def stlsq_statistics(regressor, x, y, group=None):
     """The data-dependent part of an STLSQ solve — G = ΘᵀΘ, b = ΘᵀY, Σy² per equation, n — from one pass over (x, y).
     They do not depend on the mask: `solve_SINDy` forms them once for all its thresholding iterations (the reference
-    rebuilds Θ and re-runs LAPACK on the N-row matrix every iteration, `sindy.py:260-288,319-323`)."""
+    rebuilds Θ and re-runs LAPACK on the N-row matrix every iteration, `sindy.py:260-288,319-323`). With
+    torch.distributed initialised and samples sharded over the ranks, pass `group` (or rely on the default group via
+    `solve_SINDy(..., sharded=True)`) to all-reduce them."""
     lib = regressor.library
     flags = native.SB_STEP_GRAM | native.SB_STEP_B
     with torch.no_grad():
         parts = native.unpack_step(native.train_step(x, y, None, lib, flags), lib, flags)
-        return {"G": parts["gram"], "b": parts["b"], "yy": _column_sums_of_squares(y, lib.dim),
-                "n": x.reshape(-1, lib.dim).shape[0]}
+        stats = {"G": parts["gram"], "b": parts["b"], "yy": _column_sums_of_squares(y, lib.dim),
+                 "n": x.reshape(-1, lib.dim).shape[0]}
+    return stats
 
 
 def solve_SINDy_one_step(regressor, x, y, w_sindy_reg, st_threshold, **kwargs):
@@ -321,7 +342,11 @@ def solve_SINDy_one_step(regressor, x, y, w_sindy_reg, st_threshold, **kwargs):
     driver returns an empty `residuals`, i.e. NaN, for this shape).
     '''
     lib = regressor.library
-    stats = kwargs.get('stats') or stlsq_statistics(regressor, x, y)
+    stats = kwargs.get('stats')
+    if stats is None:
+        stats = stlsq_statistics(regressor, x, y)
+        if kwargs.get('sharded'):
+            stats = allreduce_statistics(stats, kwargs.get('group'))
     with torch.no_grad():
         G, b, yy, n = stats["G"], stats["b"], stats["yy"], stats["n"]
         converged = _stlsq_update(regressor, G, b, float(w_sindy_reg) ** 2, n + lib.K, st_threshold)
@@ -337,6 +362,8 @@ def solve_SINDy(regressor, x, y, w_sindy_reg, st_threshold, max_iter=5, **kwargs
     regressor.reset_mask()
     residual = None
     stats = stlsq_statistics(regressor, x, y)   # one data pass for all thresholding iterations
+    if kwargs.get('sharded'):                   # x, y are this rank's shard: one all-reduce, identical solves everywhere
+        stats = allreduce_statistics(stats, kwargs.get('group'))
     for _ in range(max_iter):
         residual, converged = solve_SINDy_one_step(regressor, x, y, w_sindy_reg, st_threshold, stats=stats)
         if converged:

@@ -63,6 +63,59 @@ def test_sharded_step_two_ranks_gloo():
     assert ret.get(0) and ret.get(1)
 
 
+def _stlsq_worker(rank, world, port, ret):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "symmetry-ode-discovery_b200")]
+    from oracle import sindy_oracle as O
+    import sindy
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    d, p = 2, 3
+    rng = np.random.default_rng(4)
+    n = 3001
+    x = rng.uniform(-1, 1, (n, d))
+    truth = np.zeros((d, 10)); truth[0, 1], truth[0, 2], truth[1, 1], truth[1, 8] = -0.5, 1.5, 2.0, -1.0
+    y = O.theta(x, p) @ truth.T + 0.01 * rng.standard_normal((n, d))
+    cut = 1200                                     # uneven shards
+
+    def stats_of(lo, hi):                          # the kernel's job, here by the oracle: G, b, Σy², n of a shard
+        th = O.theta(x[lo:hi], p).astype(np.float64)
+        return {"G": torch.from_numpy(th.T @ th), "b": torch.from_numpy(th.T @ y[lo:hi]),
+                "yy": torch.from_numpy((y[lo:hi] ** 2).sum(0)), "n": hi - lo}
+
+    lo, hi = (0, cut) if rank == 0 else (cut, n)
+    merged = sindy.allreduce_statistics(stats_of(lo, hi))
+    whole = stats_of(0, n)
+    ok = merged["n"] == n and all(torch.allclose(merged[k], whole[k], rtol=1e-12, atol=1e-12) for k in ("G", "b", "yy"))
+    # every rank runs the identical thresholding iterations on the merged statistics
+    torch.manual_seed(0)
+    reg = sindy.SINDyRegression(d, p, False, False, threshold=0.1, device="cpu", constrain_constant=True)
+    for _ in range(5):
+        _, conv = sindy.solve_SINDy_one_step(reg, None, None, 0.0, 0.1, stats=merged)
+        if conv:
+            break
+    ok = ok and np.array_equal(reg.mask.numpy() != 0, truth != 0) and np.allclose(reg.Xi.detach().numpy() * reg.mask.numpy(), truth, atol=5e-3)
+    both = [torch.zeros_like(reg.Xi.data) for _ in range(world)]
+    dist.all_gather(both, reg.Xi.data.clone())
+    ret[rank] = bool(ok and torch.equal(both[0], both[1]))
+    dist.destroy_process_group()
+
+
+def test_sharded_stlsq_two_ranks_gloo():
+    """STLSQ over sample shards = ONE all-reduce of (G, b, Σy², n), then the same K×K solves on every rank
+    (identical masks and coefficients). The per-shard statistics come from the oracle here (no GPU)."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    port = 29500 + ((os.getpid() + 7) % 500)
+    procs = [ctx.Process(target=_stlsq_worker, args=(r, world, port, ret)) for r in range(world)]
+    for q in procs:
+        q.start()
+    for q in procs:
+        q.join(timeout=120)
+        assert q.exitcode == 0
+    assert ret.get(0) and ret.get(1)
+
+
 def test_single_process_step_matches_formula():
     sys.path[:0] = [ROOT, os.path.join(ROOT, "symmetry-ode-discovery_b200")]
     from sindy_b200 import native
