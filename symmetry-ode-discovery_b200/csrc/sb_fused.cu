@@ -635,7 +635,9 @@ int tuning_variant() {
     // shard size (1.25e7 samples, whole fit step): 15: 174.9 us, 11: 180.3, 23: 177.7, 19: 183.6. Earlier rounds of the
     // same A/B (CTA barrier per tile, one prediction chain, 1024x4 ring, unroll by 2: spills) were slower and are gone,
     // and so is a packed-monomial schedule (23 mul.f32x2 + 6 FMUL instead of 52 FMUL, same bits): 1.367 ms against
-    // 1.342 — a scalar FMUL holds the FMA pipe one cycle, a packed one two, so packing only saves issue slots.
+    // 1.342 — a scalar FMUL holds the FMA pipe one cycle, a packed one two, so packing only saves issue slots. Reading
+    // only x of the next sample ahead (3 registers; its LDS shows as the loop's largest short-scoreboard stall) made no
+    // difference either: 1.3325 against 1.3300.
     v = e ? atoi(e) : 15;
     if (v < 0 || v > 511) v = 15;
     cached.store(v, std::memory_order_release);
