@@ -547,7 +547,32 @@ def extras(native, dev, peaks, fp32_peak):
     x0d, Xid = x0[: 10 ** 5].double(), Xi.double()
     ms = timed(lambda: native.rollout(x0d, Xid, lib, 0.002, 2000, 10, "rk4", record_dx=True), reps=3)
     out["rk4_rollout_f64_1e5ics_2000steps"] = {"ic_steps_per_s": 2e8 / (ms * 1e-3), "ms": ms}
+    out["cpu_port_side_by_side"] = cpu_side_by_side()
     return out
+
+
+def cpu_side_by_side():
+    """The other two rows of the path on the host cores, bounded samples (part of the CPU-baseline reporting, SURVEY
+    §8d): the oracle port of `solve_ode_batch` (float64 RK4, K = 56) and of one `solve_SINDy_one_step` (fp32 lstsq of
+    the stacked [Θ; wI] like the reference). The port's full STLSQ does NOT recover the planted support at this size:
+    LAPACK's default rank tolerance eps·rows (0.048 at 4e5 rows) exceeds σ_min/σ_max of Θ (0.019) — see DESIGN.md §2."""
+    import numpy as np
+    from oracle import sindy_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    Xi = truth_xi("cpu").double().numpy()
+    rng = np.random.default_rng(0)
+    x0 = rng.uniform(-1, 1, (10_000, D))
+    t0 = time.perf_counter()
+    O.solve_ode_batch(O.library_rhs(Xi, P), x0, dt=0.002, num_steps=50)
+    rk = 10_000 * 49 / (time.perf_counter() - t0)
+    n = 400_000
+    x = rng.uniform(-1, 1, (n, D)).astype(np.float32)
+    y = (O.theta(x, P) @ Xi.T + 0.01 * rng.standard_normal((n, D))).astype(np.float32)
+    t0 = time.perf_counter()
+    O.stlsq_one_step(x, y, np.ones((D, K), dtype=np.float32), 0.0, 0.1, P)
+    st = n / (time.perf_counter() - t0)
+    return {"rk4_f64_ic_steps_per_s": rk, "rk4_sample": "1e4 ICs x 50 steps", "stlsq_one_step_samples_per_s": st,
+            "stlsq_sample": "4e5 samples, K = 56", "cores": torch.get_num_threads(), "kind": "port"}
 
 
 if __name__ == "__main__":
