@@ -300,3 +300,21 @@ def test_sweep_metrics_follow_eval_eq():
     np.testing.assert_allclose(agg["rmse_any"][0], (10 * r0.mean(), 10 * r0.std()), rtol=1e-6)
     ra = np.sqrt([rg["mse_all"], rb["mse_all"], rg["mse_all"]])
     np.testing.assert_allclose(agg["rmse_all_any"], (10 * ra.mean(), 10 * ra.std()), rtol=1e-6)
+
+
+@pytest.mark.parametrize("d,p", [(2, 2), (2, 3), (3, 3), (3, 5), (4, 2)])
+def test_lie_derivative_matrix_is_the_jacobian_identity(d, p):
+    """a13 / a5: the constant matrix M with J_Θ(z)·(L z) = M·Θ(z) (the reference derives it symbolically with SymPy,
+    `sindy.py:123-144`; here exponent arithmetic) checked numerically against the oracle's Jacobian of Θ for random
+    generators — for the constraint set-up (`sindy._lie_derivative_matrix`) and the regulariser (`symreg.lie_matrix`)."""
+    import sindy
+    from sindy_b200 import native, symreg
+    rng = np.random.default_rng(d * 10 + p)
+    L = rng.standard_normal((d, d))
+    z = rng.uniform(-1.2, 1.2, (64, d))
+    lhs = np.einsum("nkj,nj->nk", O.dtheta(z, p), z @ L.T)
+    th = O.theta(z.astype(np.float64), p).astype(np.float64)
+    M1 = sindy._lie_derivative_matrix(d, p, torch.tensor(L)).double().numpy()
+    M2 = symreg.lie_matrix(native.Library(d, p), torch.tensor(L)).numpy()
+    np.testing.assert_allclose(th @ M1.T, lhs, rtol=2e-5, atol=2e-5)     # M1 is stored in fp32 like the reference's
+    np.testing.assert_allclose(th @ M2.T, lhs, rtol=1e-10, atol=1e-10)
