@@ -226,8 +226,13 @@ def main():
     # into the constant bank for the next launch. Replayed as a CUDA graph. `--no-peer`: the 3-launch NCCL path.
     legacy = args.no_peer or args.no_graph
     kern_events = []
+    fallback_note = None
     if not legacy:
-        stepper = FitStepper(lib, x, dx, "adam", lr=1e-3, w_l1=w_l1, use_graph=True)
+        try:
+            stepper = FitStepper(lib, x, dx, "adam", lr=1e-3, w_l1=w_l1, use_graph=True)
+        except RuntimeError as exc:   # no peer-mapped symmetric memory on this box: the NCCL path still measures
+            legacy, fallback_note = True, f"one-launch step unavailable ({exc}); NCCL path"
+    if not legacy:
         stepper.load(Xi0, mask)
         collective = "none" if world == 1 else "in-kernel peer all-reduce over NVLink (sb_fit_step)"
         launches_per_step = 1
@@ -429,7 +434,7 @@ def main():
                    "samples_total": n_total, "samples_per_gpu": n_local, "symreg": "none",
                    "l2": "inputs (24 B/sample, %.2f GB per GPU) larger than L2; no flush" % (24 * n_local / 1e9),
                    "parallelism": f"sample-sharded x{world}, one all-reduce of {2 + D * K} fp64 sums per step",
-                   "collective": collective,
+                   "collective": collective, "fallback": fallback_note,
                    "cuda_graph": use_graph, "iterations_per_graph_replay": (unroll if not legacy else 1),
                    "final_loss": final_loss},
         "clocks": clocks, "gpu_launches": int(launches),
