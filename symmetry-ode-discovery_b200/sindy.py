@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import itertools
 import math
+import os
 
 import numpy as np
 import torch
@@ -62,6 +63,11 @@ class SINDyRegression(nn.Module):
     Arguments (as the reference): latent_dim, poly_order (reference: ≤3; here up to 5), include_sine,
     include_exp, L_list (Lie algebra generators; non-empty => equivariance-constrained Ξ = reshape(Q·β)),
     kwargs["threshold"], kwargs["device"], kwargs["constrain_constant"].
+
+    Initial parameters are drawn with `torch.randn(..., device=device)` exactly like the reference (`sindy.py:57-64`), so
+    a run on a CUDA device consumes the CUDA generator and starts where the reference ON THE SAME DEVICE starts. To
+    reproduce a run of the reference on the CPU seed for seed (the goldens of tests/golden/configs.npz), pass
+    `init_rng='cpu'` or set SINDY_B200_INIT_RNG=cpu: the same shapes are then drawn from the CPU generator and moved.
     """
 
     def __init__(self, latent_dim, poly_order, include_sine, include_exp, L_list=[], **kwargs):
@@ -76,16 +82,22 @@ class SINDyRegression(nn.Module):
         self.include_exp = bool(include_exp) and not self.constraint
         self.threshold = kwargs["threshold"]
         self.library = Library(int(latent_dim), int(poly_order), self.include_sine, self.include_exp)
+        init_rng = kwargs.get('init_rng') or os.environ.get('SINDY_B200_INIT_RNG', 'device')
+        if init_rng not in ('device', 'cpu'):
+            raise ValueError(f"init_rng must be 'device' or 'cpu', got {init_rng!r}")
+
+        def randn(*shape):
+            return torch.randn(*shape, device=device) if init_rng == 'device' else torch.randn(*shape).to(device)
 
         if self.constraint:
             print('Computing equivariance constraint...')
             self.Q = self.get_Q().to(device)
-            self.beta = nn.Parameter(torch.randn(self.Q.shape[1], device=device))
-            self.const = nn.Parameter(torch.randn(latent_dim, 1, device=device))
+            self.beta = nn.Parameter(randn(self.Q.shape[1]))
+            self.const = nn.Parameter(randn(latent_dim, 1))
             self.allow_constant = not kwargs['constrain_constant']
             self.Xi = self.get_Xi()
         else:
-            self.Xi = nn.Parameter(torch.randn(latent_dim, self.get_term_num(), device=device))
+            self.Xi = nn.Parameter(randn(latent_dim, self.get_term_num()))
         self.mask = torch.ones_like(self.Xi, device=device)
         # kept for API compatibility: names of the column groups
         self.terms = ['const', 'poly1'] + [f'poly{n}' for n in range(2, poly_order + 1)]
@@ -230,31 +242,60 @@ class SINDyRegression(nn.Module):
 # --------------------------------------------------------------------------------------------------------
 # sequentially thresholded least squares on the Gram matrix
 # --------------------------------------------------------------------------------------------------------
+def _lstsq_driver(kwargs=None):
+    """Which LAPACK driver of the reference's `torch.linalg.lstsq` (`sindy.py:288,386`) the normal-equation solves
+    follow. 'gels' (default) is what the reference gets ON A CUDA DEVICE — the only device this package runs on: plain
+    QR, no rank decision. 'gelsy' is what it gets on the CPU: rank-revealing, directions under rcond = eps32·max(M, N)
+    dropped, minimum-norm solution — needed to reproduce CPU runs of rank-deficient fits (WSINDy on Sel'kov with w = 0),
+    and wrong for large or badly scaled problems: at 2·10^4 rows the cut is 2.4e-3 in relative singular value, so a
+    library with cond(Θ) > 400 (raw-unit Lorenz data, cubic library) silently loses its small directions.
+    Selected by the keyword `lstsq_driver` of solve_SINDy* / WSINDyWrapper, else $SINDY_B200_LSTSQ."""
+    driver = (kwargs or {}).get('lstsq_driver') or os.environ.get('SINDY_B200_LSTSQ', 'gels')
+    if driver not in ('gels', 'gelsy'):
+        raise ValueError(f"lstsq driver must be 'gels' or 'gelsy', got {driver!r}")
+    return driver
+
+
 def _min_norm_solve(H: torch.Tensor, rhs: torch.Tensor, rcond: float) -> torch.Tensor:
-    """Minimum-norm solution of the symmetric PSD system H·s = rhs, dropping directions whose singular value
-    in the original least-squares matrix would fall under LAPACK gelsy's rcond·σ_max (eigenvalue < rcond²·λ_max)."""
+    """Solution of the symmetric PSD system H·s = rhs (fp64).
+
+    rcond > 0 ('gelsy'): minimum-norm solution, dropping directions whose singular value in the original least-squares
+    matrix would fall under rcond·σ_max (eigenvalue of H < rcond²·λ_max) — LAPACK gelsy's rank rule.
+    rcond == 0 ('gels'): full-rank solve. H is equilibrated first (D^-1/2 H D^-1/2 with D = diag H, i.e. the columns
+    of the least-squares matrix scaled to unit length — removes the spread between x and x^5 or between raw-unit
+    coordinates), decomposed by eigh, and only directions at the fp64 round-off level (λ < K·eps64·λ_max) are left out,
+    so an exactly singular system still returns its minimum-norm solution instead of Inf."""
     if H.numel() == 0:
         return rhs.new_zeros(rhs.shape)
-    lam, U = torch.linalg.eigh(H)
-    keep = lam > (rcond * rcond) * lam.max().clamp_min(0)
+    if rcond > 0.0:
+        lam, U = torch.linalg.eigh(H)
+        keep = lam > (rcond * rcond) * lam.max().clamp_min(0)
+        inv = torch.where(keep, 1.0 / lam.clamp_min(torch.finfo(lam.dtype).tiny), torch.zeros_like(lam))
+        return U @ (inv.unsqueeze(-1) * (U.T @ rhs)) if rhs.dim() == 2 else U @ (inv * (U.T @ rhs))
+    diag = torch.diagonal(H)
+    scale = torch.where(diag > 0, diag.clamp_min(torch.finfo(H.dtype).tiny).rsqrt(), torch.zeros_like(diag))
+    Hs = H * scale.unsqueeze(0) * scale.unsqueeze(1)
+    lam, U = torch.linalg.eigh(Hs)
+    keep = lam > H.shape[0] * torch.finfo(H.dtype).eps * lam.max().clamp_min(0)
     inv = torch.where(keep, 1.0 / lam.clamp_min(torch.finfo(lam.dtype).tiny), torch.zeros_like(lam))
-    return U @ (inv.unsqueeze(-1) * (U.T @ rhs)) if rhs.dim() == 2 else U @ (inv * (U.T @ rhs))
+    if rhs.dim() == 2:
+        return scale.unsqueeze(-1) * (U @ (inv.unsqueeze(-1) * (U.T @ (scale.unsqueeze(-1) * rhs))))
+    return scale * (U @ (inv * (U.T @ (scale * rhs))))
 
 
-def _stlsq_update(regressor, G, b, ridge, n_rows, st_threshold):
+def _stlsq_update(regressor, G, b, ridge, n_rows, st_threshold, driver='gels'):
     """Shared tail of solve_SINDy_one_step / WSINDyWrapper.solve: solve on the current support, write the
     parameters back, threshold, report convergence. G (K×K) and b (K×d) are fp64 normal-equation blocks;
     `ridge` is what is added to G's diagonal; n_rows is the row count of the reference's least-squares matrix
-    (only used for the rank tolerance)."""
+    (only used for gelsy's rank tolerance); `driver`: see _lstsq_driver."""
     d, K = regressor.latent_dim, G.shape[0]
     dev = G.device
     H = G + ridge * torch.eye(K, dtype=G.dtype, device=dev)
     mask = regressor.mask > 0.0
-    # LAPACK gelsy's default rank tolerance, eps·max(rows, cols) in the reference's fp32 — reproduced so that
-    # rank-deficient fits at the reference's sizes (WSINDy on Sel'kov) drop the same directions. It stops being a rank
-    # test when the row count grows (0.48 at 4e6 rows, 11.9 at 1e8: every direction would be dropped), so it is held at
-    # its value for 2^14 rows (2e-3) beyond that.
-    rcond = float(torch.finfo(torch.float32).eps) * min(max(n_rows, K), 1 << 14)
+    # 'gelsy': LAPACK's default rank tolerance eps·max(rows, cols) in the reference's fp32. It stops being a rank test
+    # when the row count grows (0.48 at 4e6 rows, 11.9 at 1e8: every direction would be dropped), so it is held at its
+    # value for 2^14 rows (2e-3) beyond that. 'gels': no rank decision (0).
+    rcond = float(torch.finfo(torch.float32).eps) * min(max(n_rows, K), 1 << 14) if driver == 'gelsy' else 0.0
     prev_mask = regressor.mask.clone()
 
     if bool(torch.all(mask)) and not regressor.constraint:
@@ -349,7 +390,8 @@ def solve_SINDy_one_step(regressor, x, y, w_sindy_reg, st_threshold, **kwargs):
             stats = allreduce_statistics(stats, kwargs.get('group'))
     with torch.no_grad():
         G, b, yy, n = stats["G"], stats["b"], stats["yy"], stats["n"]
-        converged = _stlsq_update(regressor, G, b, float(w_sindy_reg) ** 2, n + lib.K, st_threshold)
+        converged = _stlsq_update(regressor, G, b, float(w_sindy_reg) ** 2, n + lib.K, st_threshold,
+                                  _lstsq_driver(kwargs))
         # residual of the augmented system with the parameters just written (before masking by the new mask)
         Xi = regressor._current_Xi().to(torch.float64)
         quad = torch.einsum('ik,kl,il->i', Xi, G, Xi) - 2.0 * torch.einsum('ik,ki->i', Xi, b) + yy
@@ -365,7 +407,8 @@ def solve_SINDy(regressor, x, y, w_sindy_reg, st_threshold, max_iter=5, **kwargs
     if kwargs.get('sharded'):                   # x, y are this rank's shard: one all-reduce, identical solves everywhere
         stats = allreduce_statistics(stats, kwargs.get('group'))
     for _ in range(max_iter):
-        residual, converged = solve_SINDy_one_step(regressor, x, y, w_sindy_reg, st_threshold, stats=stats)
+        residual, converged = solve_SINDy_one_step(regressor, x, y, w_sindy_reg, st_threshold, stats=stats,
+                                                   lstsq_driver=kwargs.get('lstsq_driver'))
         if converged:
             break
     return residual
@@ -386,6 +429,7 @@ class WSINDyWrapper():
         self.t_max = float(t_max)
         self.num_test_funcs = int(num_test_funcs)
         self.regressor = regressor
+        self.kwargs = {'lstsq_driver': kwargs.get('lstsq_driver')}
         # dense V only to form the n_test×n_test weight M = V·Vᵀ once (the reference multiplies by Vᵀ on the
         # left of both sides, `sindy.py:369-370`); the data-dependent integrals never read V.
         k = torch.arange(1, num_test_funcs + 1, dtype=torch.float32, device=device).view(-1, 1)
@@ -413,7 +457,8 @@ class WSINDyWrapper():
             A = Gw.T @ MG                                        # K×K
             rhs = MG.T @ bw                                      # K×d
             K = A.shape[0]
-            converged = _stlsq_update(self.regressor, A, rhs, float(w_sindy_reg), x.shape[0] + K, st_threshold)
+            converged = _stlsq_update(self.regressor, A, rhs, float(w_sindy_reg), x.shape[0] + K, st_threshold,
+                                      _lstsq_driver(kwargs if kwargs.get('lstsq_driver') else self.kwargs))
             Xi = self.regressor._current_Xi().to(torch.float64)
             bb = torch.einsum('ji,jl,li->i', bw, self.M, bw)
             quad = torch.einsum('ik,kl,il->i', Xi, A, Xi) - 2.0 * torch.einsum('ik,ki->i', Xi, rhs) + bb

@@ -5,8 +5,10 @@ The reference's own `train.py` also runs unchanged on top of the drop-in `sindy.
 loops exist because they use the fused one-pass train step (`SINDyRegression.mse_loss`: loss and dL/dΞ from a
 single sweep over the batch, no N×K or N×d intermediate, one host sync per closure instead of 3-4) and because
 the GPU box has no copy of the reference. Optimiser, thresholding schedule, convergence tests, NaN guard,
-printed messages and checkpoint names follow the reference. `train_lassi` (LaLiGAN symmetry discovery) is
-outside the hot path and not provided.
+printed messages and checkpoint names follow the reference. `train_lassi` (LaLiGAN symmetry discovery,
+`train.py:16-269`) is outside the hot path: when a reference checkout is importable (it follows this directory on
+`sys.path`, or $SINDY_B200_REFERENCE names it) its own `train_lassi` is re-exported, running on this repo's `sindy` /
+`model_utils` operators, so that `main.py:90-91` keeps working; without a reference the name is simply absent.
 """
 from __future__ import annotations
 
@@ -20,6 +22,32 @@ from model_utils import make_fsymmreg_pttrain, make_rsymmreg_pttrain, make_symmr
 from sindy import solve_SINDy_one_step
 
 __all__ = ["train_SIGED_lbfgs", "train_SIGED", "train_WSINDy", "train_SINDy"]
+
+
+def _reference_train_module():
+    """The reference's train.py loaded under a private name (None if no reference checkout is reachable)."""
+    import importlib.util
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    for base in [os.environ.get("SINDY_B200_REFERENCE")] + list(sys.path):
+        if not base or os.path.abspath(base) == here:
+            continue
+        path = os.path.join(os.path.abspath(base), "train.py")
+        if os.path.isfile(path) and os.path.isfile(os.path.join(os.path.dirname(path), "gan.py")):
+            try:
+                spec = importlib.util.spec_from_file_location("_sindy_b200_reference_train", path)
+                mod = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(mod)
+                return mod
+            except Exception:  # noqa: BLE001  (a reference that does not import leaves train_lassi undefined)
+                return None
+    return None
+
+
+_ref_train = _reference_train_module()
+if _ref_train is not None and hasattr(_ref_train, "train_lassi"):
+    train_lassi = _ref_train.train_lassi
+    __all__.append("train_lassi")
 
 _TOL = 1e-3  # LBFGS convergence tolerance on the parameter update (reference `train.py:643`)
 
