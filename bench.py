@@ -7,17 +7,28 @@
 Workload (BASELINE.json configs[4], SURVEY.md §8d "C5"): synthetic library fit, N = 1e8 samples in total,
 d = 3, polynomial degree 5 (K = 56), X ~ U(-1,1)^3 generated on the device (seed 1234 + rank),
 dX = Θ(X)Ξ*ᵀ + 0.01·randn with the Lorenz-form Ξ*, Ξ initialised randn(3,56) with torch.manual_seed(0).
-A "step" is one iteration of the reference's Adam loop without sym-reg (`train.py:512-530`): loss = MSE + w·‖Ξ‖₁
-and dL/dΞ over ALL samples, then the Adam update of Ξ — ONE launch of the fused kernel per rank (sb_fit_step): its
-last block all-reduces the 170 packed fp64 sums over NVLink peer memory, writes loss and gradient, advances Ξ and
-packs the next Ξ⊙mask into the constant bank. Samples are sharded over the ranks (total work fixed: strong scaling). Inputs (2.4 GB) exceed the 126 MB L2, so no flush is needed between steps.
+A "step" is one iteration of the reference's Adam loop (`train.py:491-540`) WITH the linear Lie-derivative symmetry
+regulariser of `train.py:503-507` (so(3) basis, weight 0.1 — SURVEY §8d): loss = MSE + 0.1·Σ_v Σ_n ‖J_h(x_n)(v x_n) −
+v h(x_n)‖² + w·‖Ξ‖₁ and dL/dΞ over ALL samples, then the Adam update of Ξ — ONE launch of the fused kernel per rank
+(sb_fit_step): its last block all-reduces the 170 packed fp64 sums over NVLink peer memory, evaluates the MSE part from
+them and the regulariser as the quadratic form wᵀHw of the data set's Gram matrix (formed ONCE per fit by the moment
+kernel — `gram_once_per_fit_ms` in the JSON line; the data set of a fit is fixed, `train.py:626-629`), writes loss and
+gradient, advances Ξ and packs the next Ξ⊙mask for the next launch. `--no-symreg` drops the regulariser. Samples are
+sharded over the ranks (total work fixed: strong scaling). Inputs (2.4 GB) exceed the 126 MB L2: no flush needed.
 
-Printed JSON (rank 0, one line): value = whole-job samples/s with inputs resident in HBM; e2e = the same step
-through HostStreamedStep with x/dx in pinned HOST memory (H2D of every sample inside the timed region) and a
-device->host read of the loss; roofline = the fused kernel against the FP32 FMA peak measured live by
-sb_fp32_peak (not in MEASURED_PEAKS.json) and, as roofline_hbm, against the measured HBM copy bandwidth;
-cpu_baseline = the oracle port of the reference closure (torch CPU, all host threads) on a bounded sample.
-`--impl reference` times that CPU port alone (the reference is a Python package that cannot travel to the box).
+Printed JSON (rank 0, one line): value = whole-job samples/s with inputs resident in HBM; e2e = the same one-launch
+iteration (sb_fit_step through FitStepper.step_from_host) with x/dx in pinned HOST memory — H2D of every sample inside
+the timed region — and a device->host read of the loss; roofline = the fused kernel against the FP32 FMA peak measured
+live by sb_fp32_peak (not in MEASURED_PEAKS.json) and, as roofline_hbm, against the measured HBM copy bandwidth;
+cpu_baseline = the reference arm below, run as a child process on a bounded sample.
+
+`--impl reference` (rank 0 only) times the reference's OWN CPU implementation of the same step on the box's host cores:
+`SINDyRegression` imported from baseline/_ref (the unmodified reference, mirrored there by `__graft_entry__.build()`),
+its forward, `MSELoss`, the `jvp`-based regulariser of `train.py:503-507`, L1, `backward`, `torch.optim.Adam.step()`.
+The reference's library stops at degree 3, so the degree-4/5 columns of C5 are appended to ITS `terms` list in its own
+cat-of-products idiom (oracle.TorchPolyN) — `cpu_baseline.kind` = "reference"; without baseline/_ref the oracle port
+is timed instead ("port"). `extra.reference_unmodified` holds the rows the reference can run with NO extension: its
+degree-3 (K = 20) closure at 1e6 and 4e6 samples, `solve_SINDy_one_step`, `solve_ode_batch`, `WSINDyWrapper.solve`.
 """
 import argparse
 import json
@@ -29,9 +40,10 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.join(ROOT, "symmetry-ode-discovery_b200")
-for _p in (ROOT, PKG):
-    if _p not in sys.path:
-        sys.path.insert(0, _p)
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+# PKG (this repo's `sindy`, `train`, ...) is put on sys.path by the B200 arm only: the reference arm imports the
+# reference's modules of the same names from baseline/_ref
 
 import torch  # noqa: E402
 
@@ -39,6 +51,19 @@ D, P, K = 3, 5, 56
 FLOP_PER_SAMPLE = (K - 1 - D) + 2 * K * D + 3 * D + 2 * K * D   # 733: Θ, prediction, residual², r⊗Θ
 BYTES_PER_SAMPLE = 8 * D                                        # x and dx, fp32, read once
 METRIC = "SINDy train-step samples/s (fused Θ+symreg)"
+W_SYM = 0.1                                                     # weight of the so(3) Lie-derivative regulariser (§8d)
+WORKLOAD = "C5 synthetic library fit: d=3, poly degree 5 (K=56), Adam iteration on MSE + so(3) Lie-derivative reg + L1"
+
+
+def so3_basis():
+    """so(3) basis in the order of the reference's `utils.so(3)` (`utils.py:16-24`)."""
+    L = torch.zeros(3, 3, 3)
+    q = 0
+    for i in range(3):
+        for j in range(i):
+            L[q, i, j], L[q, j, i] = 1.0, -1.0
+            q += 1
+    return L
 
 
 def truth_xi(device):
@@ -109,65 +134,172 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(smax), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_closure_rate(n_cpu, budget_s=12.0, min_reps=2, max_reps=40):
-    """The oracle port of the reference closure (regressor(x) + MSELoss + L1 + backward, `train.py:645-690`,
-    with the cat-of-products Θ of `sindy.py:7-30` continued to degree 5) on all host threads."""
-    from oracle import sindy_oracle as O
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
-    g = torch.Generator().manual_seed(1234)
-    x = torch.rand(n_cpu, D, generator=g) * 2 - 1
-    dx = O.torch_theta(x, P) @ truth_xi("cpu").T + 0.01 * torch.randn(n_cpu, D, generator=g)
-    torch.manual_seed(0)
-    Xi = torch.randn(D, K)
-    mask = torch.ones(D, K)
-    O.torch_closure(x, dx, Xi, mask, P)  # warm-up
-    times = []
-    t_start = time.perf_counter()
-    while len(times) < max_reps and (len(times) < min_reps or time.perf_counter() - t_start < budget_s):
+def reference_dir():
+    for c in (os.environ.get("SINDY_B200_REFERENCE"), os.path.join(ROOT, "baseline", "_ref")):
+        if c and os.path.isfile(os.path.join(c, "sindy.py")) and os.path.isfile(os.path.join(c, "train.py")):
+            return os.path.abspath(c)
+    return None
+
+
+def _timeit(fn, budget_s, min_reps=1, max_reps=20):
+    fn()
+    ts, t_start = [], time.perf_counter()
+    while len(ts) < max_reps and (len(ts) < min_reps or time.perf_counter() - t_start < budget_s):
         t0 = time.perf_counter()
-        O.torch_closure(x, dx, Xi, mask, P)
-        times.append(time.perf_counter() - t0)
-    times.sort()
-    med = times[len(times) // 2]
-    return n_cpu / med, torch.get_num_threads(), len(times), med
+        fn()
+        ts.append(time.perf_counter() - t0)
+    ts.sort()
+    return ts[len(ts) // 2], len(ts)
 
 
 def run_reference(args, rank):
-    """`--impl reference`: the reference's CPU path (oracle port: the reference is Python and only importable in
-    the build container). Rank 0 alone works; other ranks exit."""
+    """`--impl reference`: the reference's own CPU path for the same step, all host threads, bounded sample. Rank 0
+    alone works; other ranks exit."""
     if rank != 0:
         return
+    from torch.autograd.functional import jvp
     from oracle import sindy_oracle as O
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    n_ref = args.cpu_samples
-    g = torch.Generator().manual_seed(1234)
-    x = torch.rand(n_ref, D, generator=g) * 2 - 1
-    dx = O.torch_theta(x, P) @ truth_xi("cpu").T + 0.01 * torch.randn(n_ref, D, generator=g)
-    torch.manual_seed(0)
-    Xi = torch.randn(D, K)
-    mask = torch.ones(D, K)
+    ref = reference_dir()
+    kind = "reference" if ref else "port"
+    if ref:
+        sys.path.insert(0, ref)
+        import sindy as ref_sindy
+        assert os.path.abspath(ref_sindy.__file__).startswith(ref), ref_sindy.__file__
+        torch.manual_seed(0)
+        reg = ref_sindy.SINDyRegression(D, 3, False, False, threshold=0.1, device="cpu", constrain_constant=True)
+        reg.terms += [O.TorchPolyN(4), O.TorchPolyN(5)]        # degree-4/5 columns in the reference's own idiom
+        torch.manual_seed(0)
+        reg.Xi = torch.nn.Parameter(torch.randn(D, K))
+        reg.mask = torch.ones(D, K)
+        how = ("reference's SINDyRegression.forward from baseline/_ref (terms extended to degree 5), MSELoss, jvp-based "
+               "Lie-derivative regulariser (train.py:503-507, intended [1]), L1, backward, torch.optim.Adam.step()")
+    else:
+        torch.manual_seed(0)
+        reg = O.TorchRegressor(D, P)
+        how = "oracle port of the same step (no baseline/_ref on this box)"
+    gens = so3_basis() if not args.no_symreg else []
+    mse = torch.nn.MSELoss()
+    opt = torch.optim.Adam(reg.parameters(), lr=1e-3)
+
+    def make_data(n):
+        g = torch.Generator().manual_seed(1234)
+        x = torch.rand(n, D, generator=g) * 2 - 1
+        with torch.no_grad():
+            dx = O.torch_theta(x, P) @ truth_xi("cpu").T + 0.01 * torch.randn(n, D, generator=g)
+        return x, dx
+
+    def step(x, dx, gens=gens):
+        dx_pred = reg(x)
+        loss = mse(dx_pred, dx)
+        for v in gens:
+            tangent = jvp(reg, x, torch.einsum('ij,bj->bi', v, x), create_graph=True)[1]
+            loss = loss + W_SYM * torch.norm(tangent - torch.einsum('ij,bj->bi', v, dx_pred)) ** 2
+        loss = loss + 0.0 * sum(torch.norm(p, 1) for p in reg.parameters())
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        return float(loss)
+
+    # sample size: as many of the 1e8 samples per step as keep the whole --steps/--warmup run within ~2.5 minutes
+    n_probe = 100_000
+    xp, dxp = make_data(n_probe)
+    step(xp, dxp)
+    t0 = time.perf_counter()
+    step(xp, dxp)
+    t_probe = time.perf_counter() - t0
+    budget = 150.0 / max(args.steps + args.warmup, 1)
+    n_ref = int(min(args.cpu_samples, max(50_000, n_probe * budget / t_probe)))
+    n_ref -= n_ref % 1000
+    x, dx = make_data(n_ref)
     for _ in range(args.warmup):
-        _, grad = O.torch_closure(x, dx, Xi, mask, P)
-        Xi = Xi - 1e-3 * grad
+        step(x, dx)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        _, grad = O.torch_closure(x, dx, Xi, mask, P)
-        Xi = Xi - 1e-3 * grad
+        step(x, dx)
     el = time.perf_counter() - t0
     value = n_ref * args.steps / el
-    sample = f"{n_ref} of the 1e8 samples per step (Θ is materialised: N×56 fp32 plus autograd copies)"
-    print(json.dumps({
+    sample = (f"{n_ref} of the 1e8 samples per step (the reference materialises Θ: N×56 fp32 plus autograd copies, and "
+              f"runs 2 reverse passes per generator for the jvp), {args.steps} steps")
+    result = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C5 synthetic library fit: d=3, poly degree 5 (K=56), MSE+L1 closure, loss+grad",
-                   "samples_total": int(1e8), "samples_per_step_timed": n_ref},
-        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+        "config": {"workload": WORKLOAD, "samples_total": int(1e8), "samples_per_step_timed": n_ref,
+                   "symreg": "none" if args.no_symreg else f"so(3) linear Lie-derivative regulariser, weight {W_SYM}",
+                   "step": how},
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": kind,
                          "sample": sample},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    }
+    if not args.skip_extras:
+        try:
+            result["extra"] = reference_extras(ref, step, make_data)
+        except Exception as exc:   # secondary rows must never cost the line
+            result["extra"] = {"error": repr(exc)}
+    print(json.dumps(result))
+    sys.stdout.flush()
+
+
+def reference_extras(ref, step5, make_data):
+    """Side rows on the host cores. With baseline/_ref: the UNMODIFIED reference (no extension) — its degree-3 closure
+    (`train.py:645-690`) at 1e6 and 4e6 samples, `solve_SINDy_one_step` (`sindy.py:250-315`), `solve_ode_batch`
+    (`data_utils/ode.py:7-28`), `WSINDyWrapper.solve` (`sindy.py:352-395`). Always: the degree-5 step without sym-reg."""
+    import numpy as np
+    out = {"cores": torch.get_num_threads()}
+    x, dx = make_data(500_000)
+    t, reps = _timeit(lambda: step5(x, dx, gens=[]), 8.0)
+    out["degree5_step_without_symreg"] = {"samples_per_s": 500_000 / t, "ms": 1e3 * t, "reps": reps,
+                                          "sample": "5e5 samples, K = 56"}
+    del x, dx
+    if ref is None:
+        return out
+    import sindy as ref_sindy
+    from data_utils import ode as ref_ode
+    from data_utils.selkov import selkov as ref_selkov
+    mse = torch.nn.MSELoss()
+    unmod = {}
+    for n in (1_000_000, 4_000_000):
+        g = torch.Generator().manual_seed(7)
+        xs = torch.rand(n, D, generator=g) * 2 - 1
+        ys = torch.randn(n, D, generator=g)
+        torch.manual_seed(0)
+        reg = ref_sindy.SINDyRegression(D, 3, False, False, threshold=0.1, device="cpu", constrain_constant=True)
+
+        def closure():
+            reg.zero_grad()
+            loss = mse(reg(xs), ys) + 0.0 * sum(torch.norm(p, 1) for p in reg.parameters())
+            loss.backward()
+            return loss
+
+        t, reps = _timeit(closure, 6.0 if n == 1_000_000 else 8.0)
+        unmod[f"closure_K20_n{n}"] = {"samples_per_s": n / t, "ms": 1e3 * t, "reps": reps}
+        if n == 4_000_000:
+            t0 = time.perf_counter()
+            ref_sindy.solve_SINDy_one_step(reg, xs, ys, 0.0, 0.1)
+            t = time.perf_counter() - t0
+            unmod["solve_SINDy_one_step_K20_n4000000"] = {"samples_per_s": n / t, "ms": 1e3 * t}
+        del xs, ys
+    x0 = np.random.default_rng(0).uniform(0.5, 1.0, (100_000, 2))
+    t0 = time.perf_counter()
+    ref_ode.solve_ode_batch(ref_selkov, x0, dt=0.002, num_steps=100)
+    t = time.perf_counter() - t0
+    unmod["solve_ode_batch_selkov_1e5ics_100steps"] = {"ic_steps_per_s": 1e5 * 99 / t, "ms": 1e3 * t, "dtype": "f64"}
+    T = 8000
+    tt = torch.arange(T) * 0.002
+    traj = torch.from_numpy(ref_ode.solve_ode_batch(ref_selkov, x0[:1], dt=0.002, num_steps=T)[0][:, 0]).float()
+    torch.manual_seed(0)
+    regw = ref_sindy.SINDyRegression(2, 3, False, False, threshold=0.075, device="cpu", constrain_constant=True)
+    t0 = time.perf_counter()
+    wr = ref_sindy.WSINDyWrapper(regw, tt, T * 0.002, device="cpu")
+    t_ctor = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    wr.solve(traj, 0.0, 0.075)
+    t = time.perf_counter() - t0
+    unmod["WSINDyWrapper_T8000_K10"] = {"ctor_ms": 1e3 * t_ctor, "first_solve_ms": 1e3 * t}
+    out["reference_unmodified"] = unmod
+    return out
 
 
 def main():
@@ -182,6 +314,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="do not capture the multi-GPU step in a CUDA graph")
     ap.add_argument("--no-peer", action="store_true", help="multi-GPU: NCCL all-reduce instead of the in-kernel peer all-reduce")
     ap.add_argument("--skip-extras", action="store_true")
+    ap.add_argument("--no-symreg", action="store_true", help="step without the so(3) Lie-derivative regulariser")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -193,6 +326,8 @@ def main():
     if args.warmup < 3:
         args.warmup = 3
 
+    if PKG not in sys.path:
+        sys.path.insert(0, PKG)
     import torch.distributed as dist
     from sindy_b200 import native
     from sindy_b200.dist import FitStepper, HostStreamedStep, ShardedTrainStep, bind_to_gpu_numa_node, mse_from_sums
@@ -227,9 +362,22 @@ def main():
     legacy = args.no_peer or args.no_graph
     kern_events = []
     fallback_note = None
+    sym_gens = None if args.no_symreg else list(so3_basis())
+    gram_ms = None
     if not legacy:
         try:
-            stepper = FitStepper(lib, x, dx, "adam", lr=1e-3, w_l1=w_l1, use_graph=True)
+            if sym_gens is not None:   # the Gram pass the regulariser needs ONCE per fit, timed on its own (rank's shard)
+                from sindy_b200 import symreg
+                symreg.gram(x, lib)
+                torch.cuda.synchronize()
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record()
+                symreg.gram(x, lib)
+                g1.record()
+                torch.cuda.synchronize()
+                gram_ms = g0.elapsed_time(g1)
+            stepper = FitStepper(lib, x, dx, "adam", lr=1e-3, w_l1=w_l1, use_graph=True, sym_gens=sym_gens,
+                                 w_sym=W_SYM if sym_gens is not None else 0.0)
         except RuntimeError as exc:   # no peer-mapped symmetric memory on this box: the NCCL path still measures
             legacy, fallback_note = True, f"one-launch step unavailable ({exc}); NCCL path"
     if not legacy:
@@ -342,23 +490,35 @@ def main():
         dist.all_reduce(kt, op=dist.ReduceOp.MAX)
     kern_ms = float(kt)
 
-    # ---- e2e: host buffers, H2D inside the timed region, loss read back ----
+    # ---- e2e: the same one-launch iteration with HOST buffers: H2D of every sample inside the timed region, loss read back ----
     numa_node = bind_to_gpu_numa_node(dev) if world > 1 else None   # node-local pinned buffers (one process per GPU)
-    host_step = HostStreamedStep(lib, chunk_samples=1 << 22, device=dev, flags=flags)
     xh = torch.empty(n_local, D, dtype=torch.float32, pin_memory=True)
     dxh = torch.empty(n_local, D, dtype=torch.float32, pin_memory=True)
     xh.copy_(x)
     dxh.copy_(dx)
-    Xi_e = Xi0.clone()
+    if not legacy:
+        stepper.load(Xi0, mask, reset_state=True)
+        e2e_how = ("FitStepper.step_from_host: pinned host x/dx -> device (chunked async copies) -> ONE sb_fit_step launch "
+                   "(loss, gradient, in-kernel all-reduce, Adam update); loss read back with .item()")
 
-    def e2e_step():
-        nonlocal Xi_e
-        packed = host_step(xh, dxh, Xi_e * mask)
-        if world > 1:
-            dist.all_reduce(packed)
-        loss_e, grad = mse_from_sums(packed, lib, Xi_e, mask)
-        Xi_e = Xi_e - 1e-3 * grad
-        return float(loss_e)  # device -> host read of the step's result
+        def e2e_step():
+            loss_e = stepper.step_from_host(xh, dxh)
+            return float(loss_e)  # device -> host read of the step's result
+        h2d_of = lambda: stepper.h2d_bytes  # noqa: E731
+    else:
+        host_step = HostStreamedStep(lib, chunk_samples=1 << 22, device=dev, flags=flags)
+        Xi_e = Xi0.clone()
+        e2e_how = "HostStreamedStep: pinned host x/dx -> 2 staging buffers on 2 streams -> fused kernel per chunk; .item()"
+
+        def e2e_step():
+            nonlocal Xi_e
+            packed = host_step(xh, dxh, Xi_e * mask)
+            if world > 1:
+                dist.all_reduce(packed)
+            loss_e, grad = mse_from_sums(packed, lib, Xi_e, mask)
+            Xi_e = Xi_e - 1e-3 * grad
+            return float(loss_e)
+        h2d_of = lambda: host_step.h2d_bytes  # noqa: E731
 
     e2e_step()
     barrier()
@@ -370,7 +530,7 @@ def main():
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = n_total * args.e2e_steps / float(e2e_s)
-    h2d_bytes = host_step.h2d_bytes
+    h2d_bytes = h2d_of()
     del xh, dxh
 
     # ---- sharded RK4 rollout of the same config (10^6 ICs x 2000 steps, every 10th state stored): the ICs split
@@ -428,10 +588,14 @@ def main():
         "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C5 synthetic library fit: d=3, poly degree 5 (K=56), MSE+L1 closure, loss+grad",
-                   "step": ("one Adam iteration (train.py:512-530): loss, gradient, update in ONE launch (sb_fit_step)"
+        "config": {"workload": WORKLOAD,
+                   "step": ("one Adam iteration (train.py:491-540): loss, gradient, update in ONE launch (sb_fit_step)"
                             if not legacy else "closure + SGD update (pack_w, fused kernel[, all-reduce, epilogue], axpy)"),
-                   "samples_total": n_total, "samples_per_gpu": n_local, "symreg": "none",
+                   "samples_total": n_total, "samples_per_gpu": n_local,
+                   "symreg": ("none" if (sym_gens is None or legacy) else
+                              f"so(3) linear Lie-derivative regulariser, weight {W_SYM}: quadratic form of the data set's "
+                              "Gram matrix in the kernel's epilogue; Gram formed once per fit"),
+                   "gram_once_per_fit_ms": gram_ms,
                    "l2": "inputs (24 B/sample, %.2f GB per GPU) larger than L2; no flush" % (24 * n_local / 1e9),
                    "parallelism": f"sample-sharded x{world}, one all-reduce of {2 + D * K} fp64 sums per step",
                    "collective": collective, "fallback": fallback_note,
@@ -440,28 +604,44 @@ def main():
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": 8,
                 "steps": args.e2e_steps,
-                "how": "HostStreamedStep: pinned host x/dx -> 2 staging buffers on 2 streams -> fused kernel per "
-                       "chunk; loss read back with .item()", "numa_node": numa_node},
+                "how": e2e_how, "numa_node": numa_node},
         "roofline": roofline, "roofline_hbm": roofline_hbm,
     }
 
     if rollout_sharded is not None:
         result["extra"] = {"rk4_rollout_sharded": rollout_sharded}
     if world == 1:
-        rate, cores, reps, med = cpu_closure_rate(args.cpu_samples)
-        result["cpu_baseline"] = {
-            "value": rate, "unit": "samples/s", "cores": cores, "kind": "port",
-            "sample": f"{args.cpu_samples} of the 1e8 samples, median of {reps} closures ({med * 1e3:.0f} ms each)"}
+        result["cpu_baseline"], cpu_extra = cpu_baseline_child(args)
         if not args.skip_extras:
             try:
                 result["extra"] = extras(native, dev, peaks, fp32_peak)
             except Exception as exc:   # secondary measurements must never cost the headline line
                 result["extra"] = {"error": repr(exc)}
+            result["extra"]["cpu_reference_side_by_side"] = cpu_extra
     print(json.dumps(result))
     sys.stdout.flush()
     if world > 1:
         torch.cuda.synchronize()
         os._exit(0)
+
+
+def cpu_baseline_child(args):
+    """The reference arm on a bounded sample, as a child process (it imports the REFERENCE's `sindy`, which cannot share
+    an interpreter with this repo's module of the same name): returns (cpu_baseline, its extra rows)."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "3", "--warmup", "1",
+           "--cpu-samples", str(args.cpu_samples)]
+    if args.no_symreg:
+        cmd.append("--no-symreg")
+    if args.skip_extras:
+        cmd.append("--skip-extras")
+    try:
+        res = subprocess.run(cmd, capture_output=True, text=True, timeout=900,
+                             env={k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
+        line = json.loads(res.stdout.strip().splitlines()[-1])
+        return line["cpu_baseline"], line.get("extra")
+    except Exception as exc:   # the headline line must survive a failing CPU leg
+        return {"value": None, "unit": "samples/s", "cores": os.cpu_count(), "kind": "unavailable",
+                "sample": f"reference arm failed: {exc!r}"}, None
 
 
 def extras(native, dev, peaks, fp32_peak):
@@ -552,32 +732,7 @@ def extras(native, dev, peaks, fp32_peak):
     x0d, Xid = x0[: 10 ** 5].double(), Xi.double()
     ms = timed(lambda: native.rollout(x0d, Xid, lib, 0.002, 2000, 10, "rk4", record_dx=True), reps=3)
     out["rk4_rollout_f64_1e5ics_2000steps"] = {"ic_steps_per_s": 2e8 / (ms * 1e-3), "ms": ms}
-    out["cpu_port_side_by_side"] = cpu_side_by_side()
     return out
-
-
-def cpu_side_by_side():
-    """The other two rows of the path on the host cores, bounded samples (part of the CPU-baseline reporting, SURVEY
-    §8d): the oracle port of `solve_ode_batch` (float64 RK4, K = 56) and of one `solve_SINDy_one_step` (fp32 lstsq of
-    the stacked [Θ; wI] like the reference). The port's full STLSQ does NOT recover the planted support at this size:
-    LAPACK's default rank tolerance eps·rows (0.048 at 4e5 rows) exceeds σ_min/σ_max of Θ (0.019) — see DESIGN.md §2."""
-    import numpy as np
-    from oracle import sindy_oracle as O
-    torch.set_num_threads(os.cpu_count() or 1)
-    Xi = truth_xi("cpu").double().numpy()
-    rng = np.random.default_rng(0)
-    x0 = rng.uniform(-1, 1, (10_000, D))
-    t0 = time.perf_counter()
-    O.solve_ode_batch(O.library_rhs(Xi, P), x0, dt=0.002, num_steps=50)
-    rk = 10_000 * 49 / (time.perf_counter() - t0)
-    n = 400_000
-    x = rng.uniform(-1, 1, (n, D)).astype(np.float32)
-    y = (O.theta(x, P) @ Xi.T + 0.01 * rng.standard_normal((n, D))).astype(np.float32)
-    t0 = time.perf_counter()
-    O.stlsq_one_step(x, y, np.ones((D, K), dtype=np.float32), 0.0, 0.1, P)
-    st = n / (time.perf_counter() - t0)
-    return {"rk4_f64_ic_steps_per_s": rk, "rk4_sample": "1e4 ICs x 50 steps", "stlsq_one_step_samples_per_s": st,
-            "stlsq_sample": "4e5 samples, K = 56", "cores": torch.get_num_threads(), "kind": "port"}
 
 
 if __name__ == "__main__":

@@ -197,6 +197,41 @@ def torch_theta(x: torch.Tensor, p: int, sine=False, exp=False) -> torch.Tensor:
     return torch.cat(cols, dim=-1)
 
 
+class TorchPolyN(torch.nn.Module):
+    """Degree-n block of the library as an nn.Module in the idiom of the reference's SINDyPoly2 / SINDyPoly3
+    (sindy.py:13-24: nested non-decreasing index loops, products formed left to right, one column each, torch.cat).
+    The reference stops at n = 3; appending TorchPolyN(4) and TorchPolyN(5) to `SINDyRegression.terms` extends ITS
+    forward pass to the degree-5 library of BASELINE config 5 without touching its code (bench.py --impl reference)."""
+
+    def __init__(self, n: int):
+        super().__init__()
+        self.n = n
+
+    def forward(self, x):
+        d = x.shape[-1]
+        cols = []
+        for c in itertools.combinations_with_replacement(range(d), self.n):
+            v = x[..., c[0]]
+            for j in c[1:]:
+                v = v * x[..., j]
+            cols.append(v.unsqueeze(-1))
+        return torch.cat(cols, dim=-1)
+
+
+class TorchRegressor(torch.nn.Module):
+    """Port of SINDyRegression.forward (sindy.py:79-82) for any degree: used by the benchmark's CPU arm only when no
+    reference checkout (baseline/_ref) is available."""
+
+    def __init__(self, d, p):
+        super().__init__()
+        self.p = p
+        self.Xi = torch.nn.Parameter(torch.randn(d, term_count(d, p)))
+        self.mask = torch.ones_like(self.Xi)
+
+    def forward(self, x):
+        return torch_theta(x, self.p) @ (self.Xi * self.mask).T
+
+
 def torch_closure(x, dx, Xi, mask, p, sine=False, exp=False, w_sindy_x=1.0, w_sindy_reg=0.0):
     """One evaluation of the LBFGS closure of train.py:645-690 (no sym-reg): returns (loss, Xi.grad).
     This is the CPU baseline the benchmark times ("port" of the reference closure for any degree)."""

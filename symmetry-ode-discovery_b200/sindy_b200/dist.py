@@ -345,6 +345,27 @@ class FitStepper:
         self._graphs[1].replay()
         return self.loss
 
+    def step_from_host(self, x_host: torch.Tensor, dx_host: torch.Tensor, chunk_samples: int = 1 << 22):
+        """One iteration whose samples live in (pinned) HOST memory — the host-buffer entry point of the one-launch
+        iteration: x and dx are copied host->device in chunks on the current stream into the stepper's resident
+        buffers (asynchronously when the host tensors are pinned), then ONE sb_fit_step launch consumes them. The copy
+        is PCIe-bound (2.4 GB at C5) and the kernel is ~3 % of it, so the chunks only bound the size of a single
+        transfer. Returns the loss tensor; `h2d_bytes` holds the bytes copied."""
+        if not self._loaded:
+            raise ValueError("call load(xi, mask) first")
+        if x_host.is_cuda or dx_host.is_cuda:
+            raise ValueError("step_from_host takes host tensors")
+        if x_host.shape != self.x.shape or dx_host.shape != self.dx.shape:
+            raise ValueError(f"host tensors must have the shard's shape {tuple(self.x.shape)}")
+        n = x_host.shape[0]
+        for start in range(0, n, int(chunk_samples)):
+            stop = min(start + int(chunk_samples), n)
+            self.x[start:stop].copy_(x_host[start:stop], non_blocking=True)
+            self.dx[start:stop].copy_(dx_host[start:stop], non_blocking=True)
+        self.h2d_bytes = 2 * n * self.lib.dim * 4
+        self._launch()
+        return self.loss
+
     def run(self, n_iters: int, unroll: int = 10):
         """n_iters iterations with no host involvement in between: graphs of `unroll` back-to-back launches (kernels
         inside one graph follow each other ~1 us apart, separate replays ~5 us). Returns the loss tensor of the last
