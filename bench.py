@@ -464,6 +464,38 @@ def main():
     value = n_total * args.steps / (elapsed_ms * 1e-3)
     final_loss = float(loss)
 
+    # ---- N > 1: the sharded step against an UNSHARDED recompute on rank 0 (all shards gathered on one GPU) ----
+    sharded_check = None
+    if world > 1 and not legacy:
+        stepper.load(Xi0, mask, reset_state=True)
+        l_sh = stepper.step().clone()
+        g_sh = stepper.grad.clone()
+        n_max = (n_total + world - 1) // world
+
+        def padded(t):
+            return t if t.shape[0] == n_max else torch.cat([t, t.new_zeros(n_max - t.shape[0], D)])
+        xs_all = [torch.empty(n_max, D, device=dev) for _ in range(world)] if rank == 0 else None
+        dxs_all = [torch.empty(n_max, D, device=dev) for _ in range(world)] if rank == 0 else None
+        dist.gather(padded(x), xs_all, dst=0)
+        dist.gather(padded(dx), dxs_all, dst=0)
+        if rank == 0:
+            counts = [n_total // world + (1 if r < n_total % world else 0) for r in range(world)]
+            x_all = torch.cat([t[:c] for t, c in zip(xs_all, counts)])
+            dx_all = torch.cat([t[:c] for t, c in zip(dxs_all, counts)])
+            del xs_all, dxs_all
+            one = FitStepper(lib, x_all, dx_all, "adam", lr=1e-3, w_l1=w_l1, use_graph=False, sym_gens=sym_gens,
+                             w_sym=W_SYM if sym_gens is not None else 0.0, local_only=True)
+            one.load(Xi0, mask)
+            l_one = one.step()
+            sharded_check = {
+                "loss_rel_diff": abs(float(l_sh) - float(l_one)) / abs(float(l_one)),
+                "grad_rel_diff": float((g_sh - one.grad).abs().max() / one.grad.abs().max()),
+                "how": f"one iteration at the initial parameters: {world} shards + in-kernel all-reduce vs all {n_total} "
+                       "samples gathered on rank 0 and stepped by one GPU"}
+            del one, x_all, dx_all
+        stepper.check()
+        barrier()
+
     # ---- kernel-only duration (roofline numerator) ----
     if not legacy:
         kern_ms = elapsed_ms / args.steps
@@ -599,6 +631,7 @@ def main():
                    "l2": "inputs (24 B/sample, %.2f GB per GPU) larger than L2; no flush" % (24 * n_local / 1e9),
                    "parallelism": f"sample-sharded x{world}, one all-reduce of {2 + D * K} fp64 sums per step",
                    "collective": collective, "fallback": fallback_note,
+                   "sharded_vs_unsharded": sharded_check,
                    "cuda_graph": use_graph, "iterations_per_graph_replay": (unroll if not legacy else 1),
                    "final_loss": final_loss},
         "clocks": clocks, "gpu_launches": int(launches),

@@ -15,9 +15,15 @@
  *  - the caller owns all buffers, including workspaces (`sb_workspace_bytes`); nothing is retained
  *    after the call returns except per-device constant tables;
  *  - return value: 0 = ok, negative = `sb_status`; `sb_last_error()` gives a thread-local message;
- *  - re-entrant from several host threads; ONE restriction: the specialised kernels read the coefficient matrix from a
- *    single per-device constant-bank slot, so two calls that take DIFFERENT coefficients (w / xi) must not be in flight
- *    on different streams of the same device at the same time (same coefficients, e.g. chunks of one step: fine);
+ *  - re-entrant from several host threads. The specialised kernels read the coefficient matrix from per-device
+ *    constant-bank slots: the stateless entry points (sb_train_step, sb_closure[_peer], sb_forward, sb_backward) share
+ *    scratch slot 0 — each call packs its coefficients on its own stream right before its kernel, and a call arriving
+ *    on a different stream than the previous one waits (event) for it, so concurrent streams are serialised at that
+ *    point rather than racing (inside a CUDA-graph capture the wait cannot be inserted: captured calls that use
+ *    different coefficients must then be ordered by the graph); sb_fit_step / sb_load_w keep their coefficients in
+ *    the RESIDENT slot 1, which no stateless entry point writes — forward / closure / STLSQ calls may run between two
+ *    iterations of a fit; two fits alternating on one device must re-load the slot when they take turns (sb_load_w, or
+ *    a call without SB_FIT_W_RESIDENT);
  *  - no C++ exception crosses the ABI; there is NO CPU fallback: without a CUDA device every
  *    compute entry point returns SB_ERR_CUDA.
  *
@@ -150,10 +156,13 @@ int sb_closure(const float* x, const float* dx, int64_t n, const sb_library* lib
  * epochs of all senders match and adds them in rank order, then writes the GLOBAL loss and gradient (identical bits
  * on every rank) — no collective launch, no fence, one NVLink one-way latency. peer_bufs: host array of `world` device
  * pointers (peer-mapped, e.g. torch symmetric memory), each at least sb_peer_buffer_bytes(lib, world) bytes and
- * zero-filled before the first call; epoch_dev: a zero-initialised device uint32 owned by this rank. Every rank must
- * make the same sequence of calls. Only the specialised (fused) libraries are supported: SB_ERR_UNSUPPORTED
- * otherwise. packed_out receives the GLOBAL sums. A lost peer makes the kernel give up after ~2 s instead of hanging;
- * the sums, loss and gradient of that call are then NaN (never a silently partial result). */
+ * zero-filled before the first call; epoch_dev: TWO zero-initialised device uint32 owned by this rank — [0] the epoch
+ * counter the kernel advances, [1] a sticky status word. Every rank must make the same sequence of calls. Only the
+ * specialised (fused) libraries are supported: SB_ERR_UNSUPPORTED otherwise. packed_out receives the GLOBAL sums.
+ * A lost peer makes the kernel give up after $SB_PEER_TIMEOUT_MS (default 30 000 ms) instead of hanging: the sums, loss
+ * and gradient of that call are NaN (never a silently partial result), epoch_dev[1] is set to the epoch of the first
+ * loss, and from then on sb_fit_step leaves xi, the optimiser state and the resident coefficients untouched — the host
+ * checks epoch_dev[1] at its synchronisation points and re-synchronises the ranks before clearing it. */
 int sb_closure_peer(const float* x, const float* dx, int64_t n, const sb_library* lib, const float* xi,
                     const float* mask, double w_l1, double* packed_out, float* loss_out, float* grad_out,
                     void* workspace, int64_t workspace_bytes, const void* const* peer_bufs, int world, int rank,
@@ -168,10 +177,11 @@ int64_t sb_peer_buffer_bytes(const sb_library* lib, int world);
  *   SB_OPT_ADAM: torch.optim.Adam (no weight decay, no amsgrad) in fp32 with the same operation order:
  *                m ← lerp(m, g, 1−β1); v ← β2·v + (1−β2)·g²; Ξ ← Ξ − lr/(1−β1ᵗ) · m / (√v/√(1−β2ᵗ) + eps)
  * opt_state (Adam only): 2·d·K floats [m | v] followed by one uint32 step counter t (all zero before the first step;
- * the kernel advances t). call_flags: SB_FIT_W_RESIDENT promises that the constant bank still holds Ξ⊙mask of THESE
- * parameters — true right after sb_load_w or after the previous sb_fit_step on the same device and stream, provided
- * no other call of this library that takes a coefficient matrix ran in between and xi/mask were not modified by the
- * caller; without the flag the call packs Ξ⊙mask first (one more launch). peer_bufs/world/rank/epoch_dev as in
+ * the kernel advances t). call_flags: SB_FIT_W_RESIDENT promises that the resident slot of the constant bank still holds
+ * Ξ⊙mask of THESE parameters — true right after sb_load_w or after the previous sb_fit_step on the same device and
+ * stream, provided xi/mask were not modified by the caller and no OTHER fit (sb_fit_step / sb_load_w with other
+ * parameters) ran on the device in between; the stateless entry points never touch the resident slot. Without the flag
+ * the call packs Ξ⊙mask first (one more launch). peer_bufs/world/rank/epoch_dev as in
  * sb_closure_peer (world ≤ 1: single GPU, peer_bufs/epoch_dev may be NULL): every rank applies the identical update to
  * its replica of Ξ from the identical all-reduced gradient. Libraries without a specialised kernel, or misaligned
  * inputs: SB_ERR_UNSUPPORTED (use sb_closure + the framework's optimiser). */
@@ -197,8 +207,9 @@ int sb_fit_step(const float* x, const float* dx, int64_t n, const sb_library* li
                 const sb_fit_options* opt, float* opt_state, double* packed_out, float* loss_out, float* grad_out,
                 void* workspace, int64_t workspace_bytes, const void* const* peer_bufs, int world, int rank,
                 uint32_t* epoch_dev, uint32_t call_flags, void* stream);
-/* Ξ⊙mask (mask may be NULL) into the constant bank of the specialised kernels: makes SB_FIT_W_RESIDENT true for the
- * next sb_fit_step after the caller changed xi or mask (e.g. `set_threshold`, `sindy.py:192-195`). */
+/* Ξ⊙mask (mask may be NULL) into the resident slot of the constant bank: makes SB_FIT_W_RESIDENT true for the next
+ * sb_fit_step after the caller changed xi or mask (e.g. `set_threshold`, `sindy.py:192-195`) or after another fit
+ * used the slot. */
 int sb_load_w(const sb_library* lib, const float* xi, const float* mask, void* stream);
 
 /* The same epilogue applied to packed sums that were combined across GPUs (all-reduce(sum) of

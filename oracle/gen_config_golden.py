@@ -17,6 +17,7 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
@@ -25,6 +26,37 @@ import config_runs  # noqa: E402
 REF = os.environ.get("SINDY_REFERENCE", "/root/reference")
 OUT = os.path.join(ROOT, "tests", "golden", "configs.npz")
 LOG = os.path.join(ROOT, "tests", "golden", "configs_log.txt")
+
+
+def wsindy_f64_sequence(key, seed=0):
+    """The weak-form STLSQ sequence of `main_wsindy.py:25-46` + `train.py:855-869` for the cfg's data set with the
+    least-squares solves in float64 (oracle.wsindy_one_step(solve_dtype=float64)): same seed, same random trajectory
+    and 80 % window (`main_wsindy.py:36-39`), same threshold / ridge / iteration cap as the cfg."""
+    import torch
+    from oracle import sindy_oracle as O
+    cfg = config_runs.CONFIGS[key]
+    toks = open(os.path.join(REF, "run_configs", cfg["cfg"])).read().split()
+    opt = {toks[i].lstrip("-"): toks[i + 1] for i in range(len(toks) - 1) if toks[i].startswith("--") and not toks[i + 1].startswith("--")}
+    poly, thr, w, iters = int(opt.get("poly_order", 2)), float(opt["threshold"]), float(opt["w_sindy_reg"]), int(opt["num_epochs"])
+    dt = {"lv": 0.002, "selkov": 0.002, "dosc": 0.2, "growth": 0.02}[cfg["ode"]]          # dataset.py:161-167
+    noise = float(opt["noise"])
+    x = torch.load(os.path.join(config_runs.DATA, f"{cfg['ode']}-train-noise{int(100 * noise):02d}-gp-x.pt")).float()
+    n_ics, n_steps, _ = x.shape
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    start = np.random.randint(0, n_steps - int(0.8 * n_steps))
+    traj = np.random.randint(0, n_ics)
+    win = x[traj, start:start + int(0.8 * n_steps)].numpy()
+    T = int(0.8 * n_steps)
+    mask = np.ones((2, O.term_count(2, poly)), dtype=np.float32)
+    xis, masks = [], []
+    for _ in range(iters):
+        Xi, mask, conv = O.wsindy_one_step(win, mask, w, thr, dt, T * dt, poly, solve_dtype=torch.float64)
+        xis.append(Xi)
+        masks.append(mask.copy())
+        if conv:
+            break
+    return np.stack(xis), np.stack(masks), (Xi * mask)
 
 
 def main(keys):
@@ -37,6 +69,15 @@ def main(keys):
             dt = time.time() - t0
         for k, v in res.items():
             store[f"{key}_{k}"] = v
+        if config_runs.CONFIGS[key]["script"] == "main_wsindy.py":
+            xis, masks, final = wsindy_f64_sequence(key)
+            store[f"{key}_f64_xis"], store[f"{key}_f64_masks"], store[f"{key}_f64_coefficients"] = xis, masks, final
+            if key == "C4":   # evidence that the reference's own fp32 result is not reproducible for this cfg
+                for th in ("1", "8"):
+                    with tempfile.TemporaryDirectory() as w2:
+                        r2, _ = config_runs.run_entry(key, w2, REF, dropin=False, gpu=-1,
+                                                      env={"OMP_NUM_THREADS": th, "MKL_NUM_THREADS": th})
+                    store[f"{key}_reference_threads{th}_coefficients"] = r2["coefficients"]
         tail = "\n".join(stdout.strip().splitlines()[-14:])
         logs.append(f"=== {key}: {config_runs.CONFIGS[key]['cfg']} (reference on CPU, {dt:.0f} s) ===\n{tail}\n")
         print(logs[-1], flush=True)

@@ -373,27 +373,31 @@ def wsindy_integrals(x, dt, t_max, p, sine=False, exp=False, n_test=50):
     return V.astype(np.float64) @ th, -(Vd.astype(np.float64) @ x.astype(np.float64))
 
 
-def wsindy_one_step(x, mask, w_reg, thr, dt, t_max, p, sine=False, exp=False, n_test=50):
-    """WSINDyWrapper.solve (sindy.py:352-395) with torch.linalg.lstsq in fp32 like the reference."""
+def wsindy_one_step(x, mask, w_reg, thr, dt, t_max, p, sine=False, exp=False, n_test=50, solve_dtype=torch.float32):
+    """WSINDyWrapper.solve (sindy.py:352-395) with torch.linalg.lstsq in fp32 like the reference.
+    solve_dtype=torch.float64: the same algorithm with the fp32-built test functions and data promoted to float64
+    before the products and the least-squares solve — the answer the reference's fp32 LAPACK call is a noisy estimate
+    of. Needed where the fp32 solve is not reproducible (Sel'kov, w = 0: sigma_min/sigma_max = 1.6e-4; the reference's
+    own result for BASELINE config 4 changes completely with the MKL thread count)."""
     x32 = np.asarray(x, dtype=np.float32)
     V, Vd = wsindy_test_functions(x32.shape[0], dt, t_max, n_test)
-    V, Vd = torch.from_numpy(V), torch.from_numpy(Vd)
-    xt = torch.from_numpy(x32)
-    G = V @ torch.from_numpy(theta(x32, p, sine, exp))
+    V, Vd = torch.from_numpy(V).to(solve_dtype), torch.from_numpy(Vd).to(solve_dtype)
+    xt = torch.from_numpy(x32).to(solve_dtype)
+    G = V @ torch.from_numpy(theta(x32, p, sine, exp)).to(solve_dtype)
     b = -Vd @ xt
     K, d = G.shape[1], xt.shape[1]
-    G_aug = torch.cat([V.T @ G, math.sqrt(w_reg) * torch.eye(K)], dim=0)
-    b_aug = torch.cat([V.T @ b, torch.zeros(K, d)], dim=0)
+    G_aug = torch.cat([V.T @ G, math.sqrt(w_reg) * torch.eye(K, dtype=solve_dtype)], dim=0)
+    b_aug = torch.cat([V.T @ b, torch.zeros(K, d, dtype=solve_dtype)], dim=0)
     m = torch.from_numpy(np.asarray(mask)) > 0
     if not bool(torch.all(m)):
         G_aug = torch.block_diag(*([G_aug] * d))[:, m.flatten()]
         b_aug = b_aug.T.reshape(-1)
         sol = torch.linalg.lstsq(G_aug, b_aug).solution
-        Xi = torch.zeros(d, K)
+        Xi = torch.zeros(d, K, dtype=solve_dtype)
         Xi[m] = sol
     else:
         Xi = torch.linalg.lstsq(G_aug, b_aug).solution.T
-    Xi = Xi.numpy()
+    Xi = Xi.to(torch.float32).numpy()
     new_mask = set_threshold(Xi, np.asarray(mask), thr)
     return Xi, new_mask, bool(np.allclose(new_mask, mask))
 

@@ -243,6 +243,16 @@ int sb_closure(const float* x, const float* dx, int64_t n, const sb_library* lib
   return step_epilogue(packed_out, t, xi, mask, w_l1, loss_out, grad_out, s);
 }
 
+// clock64 ticks a rank waits for its peers: $SB_PEER_TIMEOUT_MS (default 30 s) at the SM clock of the current device.
+// Long enough for lazy module loads, graph captures or a checkpoint on another rank; short enough not to wedge the GPU.
+static long long peer_timeout_ticks() {
+  double ms = 30000.0;
+  if (const char* e = getenv("SB_PEER_TIMEOUT_MS")) { const double v = atof(e); if (v > 0.0) ms = v; }
+  int dev = 0, khz = 1965000;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev);
+  return (long long)(ms * (double)khz);
+}
+
 int64_t sb_peer_buffer_bytes(const sb_library* lib, int world) {
   LibTab t;
   int s = build_table(lib, &t);
@@ -269,7 +279,8 @@ int sb_closure_peer(const float* x, const float* dx, int64_t n, const sb_library
     set_error("sb_closure_peer needs a specialised library and 16-byte aligned inputs"); return SB_ERR_UNSUPPORTED;
   }
   PeerArgs pa;
-  pa.world = world; pa.rank = rank; pa.epoch = epoch_dev;
+  pa.world = world; pa.rank = rank; pa.epoch = epoch_dev; pa.status = epoch_dev + 1;
+  pa.timeout_ticks = peer_timeout_ticks();
   for (int r = 0; r < world; ++r) {
     if (!peer_bufs[r]) { set_error("peer_bufs[%d] is NULL", r); return SB_ERR_INVALID; }
     pa.buf[r] = reinterpret_cast<double*>(const_cast<void*>(peer_bufs[r]));
@@ -301,7 +312,8 @@ int sb_fit_step(const float* x, const float* dx, int64_t n, const sb_library* li
     if (world > SB_MAX_PEERS || rank < 0 || rank >= world) {
       set_error("bad world/rank %d/%d (max %d ranks)", world, rank, SB_MAX_PEERS); return SB_ERR_INVALID;
     }
-    pa.world = world; pa.rank = rank; pa.epoch = epoch_dev;
+    pa.world = world; pa.rank = rank; pa.epoch = epoch_dev; pa.status = epoch_dev + 1;
+    pa.timeout_ticks = peer_timeout_ticks();
     for (int r = 0; r < world; ++r) {
       if (!peer_bufs[r]) { set_error("peer_bufs[%d] is NULL", r); return SB_ERR_INVALID; }
       pa.buf[r] = reinterpret_cast<double*>(const_cast<void*>(peer_bufs[r]));

@@ -210,7 +210,7 @@ struct FitArgs {
   float* m = nullptr;           // Adam first / second moments (d×K each)
   float* v = nullptr;
   unsigned int* step = nullptr; // Adam step counter (device)
-  bool w_resident = false;      // the constant bank already holds Ξ⊙mask (left there by the previous fit step)
+  bool w_resident = false;      // the resident slot already holds Ξ⊙mask (left there by the previous fit step / sb_load_w)
   const float* sym_H = nullptr; // quadratic form of the linear Lie-derivative regulariser ((d·K)² fp32) or NULL
   double w_sym = 0.0;
 };
@@ -227,7 +227,9 @@ struct PeerArgs {
   int world = 0;
   int rank = 0;
   double* buf[SB_MAX_PEERS] = {};
-  unsigned int* epoch = nullptr;
+  unsigned int* epoch = nullptr;      // [0] epoch counter, [1] sticky status (0 = ok, else the epoch a peer was lost at)
+  unsigned int* status = nullptr;     // = epoch + 1
+  long long timeout_ticks = 0;        // clock64 ticks a rank waits for its peers before giving up
 };
 
 // specialised (compile-time library, register-resident, TMA-staged) fused train step.

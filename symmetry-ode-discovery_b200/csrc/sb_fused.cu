@@ -31,6 +31,22 @@ namespace sb {
 
 namespace {
 
+// W = Ξ⊙mask lives in the constant bank so that the kernels read it through the uniform datapath (LDCU -> UR operands).
+// The bank is cut in kWSlots slots of kWSlotFloats floats (every specialised library needs <= 2·d·K2 = 168):
+//   slot 0      scratch of the stateless calls (sb_train_step, sb_closure[_peer], sb_forward, sb_backward): each packs its
+//               W right before its kernel ON ITS STREAM, so calls that are stream-ordered with each other never see a
+//               foreign W; a call arriving on another stream first waits for the previous user (guard_scratch below);
+//   slot 1      resident coefficients of the one-launch iteration (sb_fit_step / sb_load_w): the kernel's epilogue writes
+//               the next Ξ⊙mask back into it and no stateless call touches it — a validation forward or an STLSQ closure
+//               between two iterations cannot clobber it. Two FITS that alternate on one device share it: the host side
+//               keeps a generation count per device and re-packs when the slot was last loaded by somebody else
+//               (native.load_w / FitStepper._own_slot).
+// The slot is a TEMPLATE parameter of the kernel, not an argument: with an immediate address ptxas fetches W with
+// LDCU.128 (27 per sample at d = 3, K = 56); a uniform-register offset makes it fall back to 84 LDCU.64.
+constexpr int kWSlots = 2;
+constexpr int kWSlotFloats = 512;                      // 2 KB per slot (every specialised library needs <= 168 floats)
+constexpr int kWSlotPairs = kWSlotFloats / 2;
+static_assert(kWSlots * kWSlotFloats <= kConstW, "slots exceed the constant array");
 __constant__ float2 c_w2[kConstW / 2];
 
 unsigned long long* g_trace = nullptr;   // set by sb_debug_trace (timeline of the fused kernel's phases)
@@ -78,10 +94,11 @@ struct Cfg {
 enum { LEFT_RESIDUAL = 0, LEFT_DX = 1 };
 
 // one sample: expand Θ, predict, accumulate r ⊗ Θ
-template <int D, int P, int LEFT, int VAR>
+template <int D, int P, int LEFT, int VAR, int SLOT>
 __device__ __forceinline__ void accumulate_sample(const float (&xs)[D], const float (&ds)[D],
                                                   float2 (&acc)[D][Cfg<D, P, VAR>::K2], float& lacc) {
   using C = Cfg<D, P, VAR>;
+  constexpr int w_off = SLOT * kWSlotPairs;
   float m[C::K];
   expand_poly<D, P>(xs, m);
   float2 m2[C::K2];
@@ -98,7 +115,7 @@ __device__ __forceinline__ void accumulate_sample(const float (&xs)[D], const fl
       static_for<0, NC>([&](auto c) { pred[c] = make_float2(0.f, 0.f); });
       static_for<0, C::K2>([&](auto kc) {
         constexpr int kk = kc;
-        pred[kk % NC] = __ffma2_rn(c_w2[i * C::K2 + kk], m2[kk], pred[kk % NC]);
+        pred[kk % NC] = __ffma2_rn(c_w2[w_off + i * C::K2 + kk], m2[kk], pred[kk % NC]);
       });
       const float s = ((pred[0].x + pred[0].y) + (pred[1].x + pred[1].y)) + ((pred[2].x + pred[2].y) + (pred[3].x + pred[3].y));
       r[i] = s - ds[i];
@@ -118,7 +135,7 @@ __device__ __forceinline__ void accumulate_sample(const float (&xs)[D], const fl
       constexpr int kk = kc;
       static_for<0, D>([&](auto ic) {
         constexpr int i = ic;
-        pred[i][kk % NC] = __ffma2_rn(c_w2[i * C::K2 + kk], m2[kk], pred[i][kk % NC]);
+        pred[i][kk % NC] = __ffma2_rn(c_w2[w_off + i * C::K2 + kk], m2[kk], pred[i][kk % NC]);
       });
     });
     static_for<0, D>([&](auto i) {
@@ -173,7 +190,7 @@ struct FusedArgs {
   // optional optimiser update fused into that epilogue (sb_fit_step): Ξ is advanced in place and Ξ⊙mask is packed
   // into the constant bank for the NEXT launch, so a whole training iteration is this one kernel
   FitArgs fit;
-  float* w_const;     // device address of the packed constant slot (c_w2)
+  float* w_const;     // device (global-alias) address of THIS call's constant slot
   // optional linear Lie-derivative regulariser as a quadratic form of w = vec(Ξ⊙mask): w_sym·wᵀHw (sb_fit_options)
   const float* sym_H; // (d·K)² fp32, symmetric, row-major
   double w_sym;
@@ -182,7 +199,7 @@ struct FusedArgs {
   PeerArgs peer;
 };
 
-template <int D, int P, int LEFT, int VAR>
+template <int D, int P, int LEFT, int VAR, int SLOT>
 __global__ void __launch_bounds__(Cfg<D, P, VAR>::kThreads, Cfg<D, P, VAR>::kMinBlocks)
 fused_step_kernel(FusedArgs a) {
   using C = Cfg<D, P, VAR>;
@@ -276,14 +293,14 @@ fused_step_kernel(FusedArgs a) {
         static_for<0, D>([&](auto q) { xs[q] = xn[q]; ds[q] = dn[q]; });
         const int jn = j + C::kThreads;
         if (jn < cnt) static_for<0, D>([&](auto q) { xn[q] = sx[jn * D + q]; dn[q] = sd[jn * D + q]; });
-        accumulate_sample<D, P, LEFT, VAR>(xs, ds, acc, lacc);
+        accumulate_sample<D, P, LEFT, VAR, SLOT>(xs, ds, acc, lacc);
       }
     } else {
 #pragma unroll 1
       for (int j = tid; j < cnt; j += C::kThreads) {
         float xs[D], ds[D];
         static_for<0, D>([&](auto q) { xs[q] = sx[j * D + q]; ds[q] = sd[j * D + q]; });
-        accumulate_sample<D, P, LEFT, VAR>(xs, ds, acc, lacc);
+        accumulate_sample<D, P, LEFT, VAR, SLOT>(xs, ds, acc, lacc);
       }
     }
     if constexpr (C::kEmptyBarriers) {
@@ -304,7 +321,7 @@ fused_step_kernel(FusedArgs a) {
     if (j < a.n) {
       float xs[D], ds[D];
       static_for<0, D>([&](auto q) { xs[q] = __ldg(a.x + j * D + q); ds[q] = __ldg(a.dx + j * D + q); });
-      accumulate_sample<D, P, LEFT, VAR>(xs, ds, acc, lacc);
+      accumulate_sample<D, P, LEFT, VAR, SLOT>(xs, ds, acc, lacc);
     }
   }
 
@@ -460,6 +477,7 @@ fused_step_kernel(FusedArgs a) {
   // in rank order (identical bits on every rank). One NVLink one-way latency instead of store + system fence + flag.
   // Two parities suffice: a rank can run at most one step ahead, because finishing step e+1 needs every peer's lines
   // of e+1, which a peer only sends after it has read the lines of step e.
+  bool peer_lost = false;
   if (a.peer.world > 1) {
     constexpr int NVX = C::NV + 1;
     static_assert(NVX <= C::kThreads, "one exchanged value per thread");
@@ -477,6 +495,8 @@ fused_step_kernel(FusedArgs a) {
       }
       double v = 0.0;
       const long long t0 = clock64();
+      const long long limit = a.peer.timeout_ticks;
+      bool lost = false;
       for (int r = 0; r < world; ++r) {
         const uint4* src = reinterpret_cast<const uint4*>(a.peer.buf[rank]) + (size_t)(par * world + r) * NVX + tid;
         unsigned int q0, q1, q2, q3;
@@ -485,16 +505,20 @@ fused_step_kernel(FusedArgs a) {
                        : "=r"(q0), "=r"(q1), "=r"(q2), "=r"(q3)
                        : "l"(src)
                        : "memory");
-        } while ((q1 != epoch || q3 != epoch) && (clock64() - t0) < 4000000000ll);   // ~2 s: never hang on a lost peer
-        // a peer that never arrived must not pass silently: its contribution poisons the sums, so loss, gradient and
-        // (sb_fit_step) the parameters come out NaN on this rank
-        if (q1 != epoch || q3 != epoch) v = __longlong_as_double(0x7ff8000000000000ll);
+        } while ((q1 != epoch || q3 != epoch) && (clock64() - t0) < limit);   // bounded: never hang the GPU on a lost peer
+        // a peer that never arrived must not pass silently: the sums of this call are poisoned (NaN loss / gradient) ...
+        if (q1 != epoch || q3 != epoch) { v = __longlong_as_double(0x7ff8000000000000ll); lost = true; }
         v += __longlong_as_double((long long)(((unsigned long long)q2 << 32) | (unsigned long long)q0));
       }
       fin[tid] = v;
+      // ... and the failure is recorded in the rank's sticky status word (epoch of the first loss), which the host reads at
+      // its sync points (FitStepper.check); the optimiser update below is skipped so that Ξ, the Adam moments and the
+      // resident W stay at their last good values instead of turning NaN for good
+      if (lost) atomicCAS(a.peer.status, 0u, epoch);
     }
     __syncthreads();
     if (tid == 0) *a.peer.epoch = epoch;   // after the barrier: every thread has read the old value long ago
+    peer_lost = (*reinterpret_cast<volatile unsigned int*>(a.peer.status) != 0u);
   }
   const double n_total = fin[C::NV];
   stamp(a.trace, 5);
@@ -574,7 +598,7 @@ fused_step_kernel(FusedArgs a) {
       const float g = (float)(fin[e] * (2.0 / denom) * a.w_mse * (double)mk + a.w_l1 * sgn +
                               a.w_sym * 2.0 * sym_hw * (double)mk);
       if (a.grad_out) a.grad_out[e] = g;
-      if (a.fit.kind != SB_OPT_NONE) {
+      if (a.fit.kind != SB_OPT_NONE && !peer_lost) {
         float xn;
         if (a.fit.kind == SB_OPT_ADAM) {
           // the arithmetic of torch's Adam in fp32: lerp, mul+addcmul, sqrt / sqrt(bc2) + eps, addcdiv
@@ -603,7 +627,7 @@ fused_step_kernel(FusedArgs a) {
         for (int wq = 0; wq < C::kWarps; ++wq) { t += l1w[wq]; ts += lsw[wq]; }
         *a.loss_out = (float)(a.w_mse * fin[C::NV - 1] / denom + a.w_l1 * t + a.w_sym * ts);
       }
-      if (a.fit.kind == SB_OPT_ADAM) *a.fit.step = ep_step + 1u;
+      if (a.fit.kind == SB_OPT_ADAM && !peer_lost) *a.fit.step = ep_step + 1u;
     }
   }
   stamp(a.trace, 6);
@@ -645,11 +669,14 @@ int tuning_variant() {
   return v;
 }
 
-template <int D, int P, int LEFT, int VAR>
-int launch_fused_var(FusedArgs a, void* ws, int64_t ws_bytes, cudaStream_t s) {
+template <int D, int P, int LEFT, int VAR, int SLOT = 0>
+int launch_fused_var(FusedArgs a, void* ws, int64_t ws_bytes, cudaStream_t s, int slot = 0) {
   using C = Cfg<D, P, VAR>;
-  auto kern = fused_step_kernel<D, P, LEFT, VAR>;
-  static int grid_cached[64] = {0};  // per device
+  if constexpr (LEFT == LEFT_RESIDUAL && SLOT == 0) {   // the residual kernel exists once per coefficient slot
+    if (slot == 1) return launch_fused_var<D, P, LEFT, VAR, 1>(a, ws, ws_bytes, s, 1);
+  }
+  auto kern = fused_step_kernel<D, P, LEFT, VAR, SLOT>;
+  static int grid_cached[64] = {0};  // per device (and per instantiation: this is a function template)
   int dev = 0;
   SB_CUDA_TRY(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64) { set_error("device index %d out of range", dev); return SB_ERR_INVALID; }
@@ -689,43 +716,74 @@ int launch_fused_var(FusedArgs a, void* ws, int64_t ws_bytes, cudaStream_t s) {
 }
 
 template <int D, int P, int LEFT>
-int launch_fused(const FusedArgs& a, void* ws, int64_t ws_bytes, cudaStream_t s) {
+int launch_fused(const FusedArgs& a, void* ws, int64_t ws_bytes, cudaStream_t s, int slot = 0) {
   if constexpr (D == 3 && P == 5) {  // the headline shape carries the A/B variants
     switch (tuning_variant()) {
-      case 11: return launch_fused_var<D, P, LEFT, 11>(a, ws, ws_bytes, s);
-      case 19: return launch_fused_var<D, P, LEFT, 19>(a, ws, ws_bytes, s);
-      case 23: return launch_fused_var<D, P, LEFT, 23>(a, ws, ws_bytes, s);
-      case 47: return launch_fused_var<D, P, LEFT, 47>(a, ws, ws_bytes, s);
-      case 143: return launch_fused_var<D, P, LEFT, 143>(a, ws, ws_bytes, s);
-      default: return launch_fused_var<D, P, LEFT, 15>(a, ws, ws_bytes, s);
+      case 11: return launch_fused_var<D, P, LEFT, 11>(a, ws, ws_bytes, s, slot);
+      case 19: return launch_fused_var<D, P, LEFT, 19>(a, ws, ws_bytes, s, slot);
+      case 23: return launch_fused_var<D, P, LEFT, 23>(a, ws, ws_bytes, s, slot);
+      case 47: return launch_fused_var<D, P, LEFT, 47>(a, ws, ws_bytes, s, slot);
+      case 143: return launch_fused_var<D, P, LEFT, 143>(a, ws, ws_bytes, s, slot);
+      default: return launch_fused_var<D, P, LEFT, 15>(a, ws, ws_bytes, s, slot);
     }
   }
-  return launch_fused_var<D, P, LEFT, 5>(a, ws, ws_bytes, s);  // small libraries: empty-barrier ring + folded reduction
+  return launch_fused_var<D, P, LEFT, 5>(a, ws, ws_bytes, s, slot);  // small libraries: empty-barrier ring + folded reduction
 }
 
-// device address of the packed constant slot on the current device
-int const_slot(float** out) {
+// device (global-alias) address of constant slot `slot` on the current device
+int const_slot(int slot, float** out) {
   static float* base[64] = {nullptr};
   int dev = 0;
   SB_CUDA_TRY(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64) { set_error("device index %d out of range", dev); return SB_ERR_INVALID; }
+  if (slot < 0 || slot >= kWSlots) { set_error("coefficient slot %d out of range (0..%d)", slot, kWSlots - 1); return SB_ERR_INVALID; }
   std::lock_guard<std::mutex> lock(g_init_mutex);
   if (!base[dev]) {
     void* p = nullptr;
     SB_CUDA_TRY(cudaGetSymbolAddress(&p, c_w2));
     base[dev] = reinterpret_cast<float*>(p);
   }
-  *out = base[dev];
+  *out = base[dev] + (size_t)slot * kWSlotFloats;
+  return SB_OK;
+}
+
+// The scratch slot (0) is shared by every stateless call on the device. Calls on ONE stream are ordered by the stream.
+// A call arriving on a different stream than the previous user's must not repack the slot while that user's kernel may
+// still be reading it: it waits for an event recorded behind the previous user (no-op in the common single-stream case;
+// skipped while either stream is being captured into a CUDA graph — captured work replays in graph order).
+struct ScratchUser { cudaStream_t stream = nullptr; cudaEvent_t ev = nullptr; bool used = false; };
+ScratchUser g_scratch[64];
+
+int guard_scratch(cudaStream_t s) {
+  int dev = 0;
+  SB_CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) { set_error("device index %d out of range", dev); return SB_ERR_INVALID; }
+  std::lock_guard<std::mutex> lock(g_init_mutex);
+  ScratchUser& u = g_scratch[dev];
+  if (u.used && u.stream != s) {
+    cudaStreamCaptureStatus a = cudaStreamCaptureStatusNone, b = cudaStreamCaptureStatusNone;
+    SB_CUDA_TRY(cudaStreamIsCapturing(s, &a));
+    if (cudaStreamIsCapturing(u.stream, &b) != cudaSuccess) { cudaGetLastError(); b = cudaStreamCaptureStatusNone; u.used = false; }
+    if (u.used && a == cudaStreamCaptureStatusNone && b == cudaStreamCaptureStatusNone) {
+      if (!u.ev) SB_CUDA_TRY(cudaEventCreateWithFlags(&u.ev, cudaEventDisableTiming));
+      if (cudaEventRecord(u.ev, u.stream) == cudaSuccess) SB_CUDA_TRY(cudaStreamWaitEvent(s, u.ev, 0));
+      else cudaGetLastError();   // the previous user's stream no longer exists: its work has completed
+    }
+  }
+  u.stream = s;
+  u.used = true;
   return SB_OK;
 }
 
 // Ξ [⊙ mask] -> constant slot, one tiny launch on the stream (replaces a D2D cudaMemcpyToSymbolAsync + a mul)
 template <int D, int P>
-int upload_w(const float* xi, const float* mask, cudaStream_t s) {
+int upload_w(const float* xi, const float* mask, int slot, cudaStream_t s) {
   using C = Cfg<D, P>;
+  static_assert(D * C::K2 * 2 <= kWSlotFloats, "a coefficient slot holds d x 2*K2 floats");
   float* base = nullptr;
-  int st = const_slot(&base);
+  int st = const_slot(slot, &base);
   if (st != SB_OK) return st;
+  if (slot == 0) { st = guard_scratch(s); if (st != SB_OK) return st; }
   const int total = D * C::K2 * 2;
   pack_w_kernel<<<(total + 255) / 256, 256, 0, s>>>(xi, mask, base, D, C::K, C::K2);
   SB_LAUNCH_CHECK("pack_w_kernel");
@@ -742,7 +800,8 @@ int run_fused(const float* x, const float* dx, int64_t n, const float* w, const 
   const bool resid = flags & (SB_STEP_LOSS | SB_STEP_GRAD);
   if (resid) {
     int st = SB_OK;
-    if (!(fit && fit->w_resident)) st = upload_w<D, P>(w, mask, s);
+    const int slot = (fit && fit->kind != SB_OPT_NONE) ? 1 : 0;
+    if (!(fit && fit->w_resident)) st = upload_w<D, P>(w, mask, slot, s);
     if (st != SB_OK) return st;
     a.out_off = 2; a.out_transposed = 0; a.write_header = 1;
     if (co) {
@@ -751,11 +810,11 @@ int run_fused(const float* x, const float* dx, int64_t n, const float* w, const 
     if (fit && fit->kind != SB_OPT_NONE) {
       a.fit = *fit;
       a.sym_H = fit->sym_H; a.w_sym = fit->w_sym;
-      st = const_slot(&a.w_const);
+      st = const_slot(slot, &a.w_const);
       if (st != SB_OK) return st;
     }
     if (peer) a.peer = *peer;
-    st = launch_fused<D, P, LEFT_RESIDUAL>(a, ws, ws_bytes, s);
+    st = launch_fused<D, P, LEFT_RESIDUAL>(a, ws, ws_bytes, s, slot);
     if (st != SB_OK) return st;
     a.loss_out = nullptr; a.grad_out = nullptr; a.peer = PeerArgs{}; a.fit = FitArgs{}; a.sym_H = nullptr;
   }
@@ -797,7 +856,7 @@ __global__ void __launch_bounds__(256) forward_spec_kernel(const float* __restri
 
 template <int D, int P>
 int run_forward(const float* x, int64_t n, const float* w, float* y, cudaStream_t s) {
-  int st = upload_w<D, P>(w, nullptr, s);
+  int st = upload_w<D, P>(w, nullptr, 0, s);
   if (st != SB_OK) return st;
   int64_t blocks = (n + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
@@ -866,7 +925,7 @@ int64_t fused_workspace_bytes(const LibTab& t) {
 }
 
 int fused_load_w(const LibTab& t, const float* xi, const float* mask, cudaStream_t s) {
-#define X(D, P) if (t.d == D && t.n_poly == n_poly_terms(D, P)) return upload_w<D, P>(xi, mask, s);
+#define X(D, P) if (t.d == D && t.n_poly == n_poly_terms(D, P)) return upload_w<D, P>(xi, mask, 1, s);
   SB_FUSED_SHAPES(X)
 #undef X
   set_error("no fused kernel for d=%d K=%d", t.d, t.K);

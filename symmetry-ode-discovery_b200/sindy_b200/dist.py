@@ -91,7 +91,7 @@ class PeerExchange:
         self.buf.zero_()
         self.handle = symm_mem.rendezvous(self.buf, group)
         self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
-        self.epoch = torch.zeros(1, dtype=torch.int32, device=device)
+        self.epoch = torch.zeros(2, dtype=torch.int32, device=device)   # [epoch counter, sticky status word]
         torch.cuda.synchronize(device)
         dist.barrier(group)       # every rank's buffer is zeroed before anybody's kernel may write into it
 
@@ -258,8 +258,10 @@ class FitStepper:
 
     def __init__(self, lib: Library, x: torch.Tensor, dx: torch.Tensor, kind: str = "adam", lr: float = 1e-3,
                  betas=(0.9, 0.999), eps: float = 1e-8, w_mse: float = 1.0, w_l1: float = 0.0, group=None,
-                 use_graph: bool = True, use_peer: bool = True, sym_gens=None, w_sym: float = 0.0):
+                 use_graph: bool = True, use_peer: bool = True, sym_gens=None, w_sym: float = 0.0,
+                 local_only: bool = False):
         self.lib, self.x, self.dx = lib, x, dx
+        world = 1 if local_only else _world(group)   # local_only: this process's data alone, even under torchrun
         # linear Lie-derivative regulariser (`train.py:503-507`): the Gram matrix of the (fixed) data set is formed
         # once — one pass of the moment kernel per rank and one all-reduce — and turned into the quadratic form H;
         # every iteration then evaluates w_sym·wᵀHw and its gradient inside the kernel's epilogue
@@ -267,7 +269,7 @@ class FitStepper:
         if sym_gens is not None and len(sym_gens) > 0 and w_sym != 0.0:
             from . import symreg
             G = symreg.gram(x, lib).clone()
-            if _world(group) > 1:
+            if world > 1:
                 dist.all_reduce(G, op=dist.ReduceOp.SUM, group=group)
             self.sym_quad = symreg.quadratic_form(lib, sym_gens, G).to(torch.float32).contiguous()
         self.kind, self.lr, self.betas, self.eps, self.w_mse, self.w_l1 = kind, lr, betas, eps, w_mse, w_l1
@@ -280,7 +282,7 @@ class FitStepper:
         self.loss = torch.empty((), dtype=torch.float32, device=dev)
         self.grad = torch.empty(d, K, dtype=torch.float32, device=dev)
         self.peer = None
-        if _world(group) > 1:
+        if world > 1:
             self.peer = PeerExchange.create(lib, dev, group) if use_peer else None
             if self.peer is None:
                 raise RuntimeError("FitStepper over several ranks needs the peer exchange (symmetric memory); use "
@@ -290,6 +292,9 @@ class FitStepper:
         self._graphs = {}
         self._warm = False
         self._loaded = False
+        self._slot_gen = -1       # generation of the device's resident coefficient slot when this stepper last loaded it
+        if self.peer is not None:
+            dist.barrier(group)   # nobody launches an exchanging kernel before every rank has built its stepper
 
     def load(self, xi: torch.Tensor, mask: Optional[torch.Tensor] = None, reset_state: bool = False):
         self.xi.copy_(xi)
@@ -297,8 +302,25 @@ class FitStepper:
             self.mask.copy_(mask)
         if reset_state:
             self.state.zero_()
-        native.load_w(self.xi, self.mask, self.lib)
+        self._slot_gen = native.load_w(self.xi, self.mask, self.lib)
         self._loaded = True
+
+    def _own_slot(self):
+        """Before every launch / replay: if somebody else has loaded this stepper's slot since (only possible when more
+        than 7 steppers share a device), re-pack the coefficients — xi and mask live in this stepper's own memory."""
+        if native.slot_generation(self.x.device, self.w_slot) != self._slot_gen:
+            self._slot_gen = native.load_w(self.xi, self.mask, self.lib)
+
+    def check(self):
+        """Raises if a peer was lost during an in-kernel exchange (sticky status word of sb_fit_step; reading it
+        synchronises the device). After a loss the kernels leave Ξ, the optimiser state and the resident coefficients
+        untouched; the ranks must be re-synchronised (load) before the word is cleared."""
+        if self.peer is not None:
+            st = int(self.peer.epoch[1])
+            if st != 0:
+                raise native.SindyB200Error(
+                    f"rank {self.peer.rank}: a peer did not arrive at the in-kernel all-reduce of epoch {st} within "
+                    f"$SB_PEER_TIMEOUT_MS; parameters were left at their last good values")
 
     def _launch(self, loss=None):
         p = self.peer
@@ -322,7 +344,7 @@ class FitStepper:
             torch.cuda.current_stream().wait_stream(side)
             self.xi.copy_(keep_xi)
             self.state.copy_(keep_state)
-            native.load_w(self.xi, self.mask, self.lib)
+            self._slot_gen = native.load_w(self.xi, self.mask, self.lib)
             self._warm = True
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
@@ -337,6 +359,7 @@ class FitStepper:
         """One iteration; returns the (static) loss tensor: the value at the parameters BEFORE the update."""
         if not self._loaded:
             raise ValueError("call load(xi, mask) first")
+        self._own_slot()
         if not self._use_graph:
             self._launch()
             return self.loss
@@ -357,6 +380,7 @@ class FitStepper:
             raise ValueError("step_from_host takes host tensors")
         if x_host.shape != self.x.shape or dx_host.shape != self.dx.shape:
             raise ValueError(f"host tensors must have the shard's shape {tuple(self.x.shape)}")
+        self._own_slot()
         n = x_host.shape[0]
         for start in range(0, n, int(chunk_samples)):
             stop = min(start + int(chunk_samples), n)
@@ -372,6 +396,7 @@ class FitStepper:
         iteration; `loss_hist[:unroll]` holds the losses of the last full group."""
         if not self._loaded:
             raise ValueError("call load(xi, mask) first")
+        self._own_slot()
         if not self._use_graph:
             for _ in range(n_iters):
                 self._launch()

@@ -356,12 +356,38 @@ def fit_state(lib: Library, device) -> torch.Tensor:
     return torch.zeros(2 * lib.dim * lib.K + 1, dtype=torch.float32, device=device)
 
 
-def load_w(xi: torch.Tensor, mask: Optional[torch.Tensor], lib: Library) -> None:
-    """Ξ⊙mask into the constant bank of the specialised kernels (makes SB_FIT_W_RESIDENT true)."""
+# The RESIDENT coefficient slot of the one-launch iteration (include/sindy_b200.h): sb_fit_step reads Ξ⊙mask from it and
+# its epilogue writes the next one back; the stateless calls (forward, closure, STLSQ passes) use the scratch slot and
+# never touch it. Only another FIT on the same device can: every load_w bumps a per-device generation and returns it; a
+# stepper compares it with the generation it last saw before each launch / graph replay and re-packs on a mismatch
+# (FitStepper._own_slot, train._adam_fused_epochs) — xi and mask live in the stepper's own memory, so that is always
+# possible and costs one tiny launch.
+_slot_lock = threading.Lock()
+_slot_generation = {}   # device index -> counter bumped by every load of the resident slot
+
+
+def bump_slot_generation(device) -> int:
+    idx = torch.device(device).index or 0
+    with _slot_lock:
+        g = _slot_generation.get(idx, 0) + 1
+        _slot_generation[idx] = g
+        return g
+
+
+def slot_generation(device) -> int:
+    idx = torch.device(device).index or 0
+    with _slot_lock:
+        return _slot_generation.get(idx, 0)
+
+
+def load_w(xi: torch.Tensor, mask: Optional[torch.Tensor], lib: Library) -> int:
+    """Ξ⊙mask into the resident slot of the constant bank (makes SB_FIT_W_RESIDENT true). Returns the slot's new
+    generation: whoever loaded it last owns it."""
     xi = _f32c(xi, "xi")
     mk = _f32c(mask, "mask") if mask is not None else None
     with torch.cuda.device(xi.device):
         _check(load().sb_load_w(ctypes.byref(lib.c()), xi.data_ptr(), _ptr(mk), _stream(xi.device)), "sb_load_w")
+    return bump_slot_generation(xi.device)
 
 
 def fit_step(x: torch.Tensor, dx: torch.Tensor, xi: torch.Tensor, mask: Optional[torch.Tensor], lib: Library,
@@ -373,7 +399,8 @@ def fit_step(x: torch.Tensor, dx: torch.Tensor, xi: torch.Tensor, mask: Optional
     """One iteration of the Adam (or SGD) loop `train.py:512-530` in ONE launch: loss and dL/dΞ at the current
     parameters, then `xi` (fp32 CUDA, contiguous) is advanced IN PLACE. Returns (loss, grad, packed). `state`
     = fit_state(lib) for Adam. With peer_ptrs the samples are sharded over the ranks (see closure_peer).
-    sym_quad (symreg.quadratic_form) adds w_sym × the linear Lie-derivative regulariser of the data set."""
+    sym_quad (symreg.quadratic_form) adds w_sym × the linear Lie-derivative regulariser of the data set.
+    w_resident=False packs Ξ⊙mask into the resident slot first (and takes the slot over: its generation is bumped)."""
     xf = _flat(_f32c(x, "x"), lib.dim, "x")
     dxf = _flat(_f32c(dx, "dx"), lib.dim, "dx")
     if xf.data_ptr() % 16:       # the TMA-staged kernel needs 16-byte aligned inputs (a view at an odd offset)
@@ -412,6 +439,8 @@ def fit_step(x: torch.Tensor, dx: torch.Tensor, xi: torch.Tensor, mask: Optional
                                   _ptr(mk), ctypes.byref(opt), _ptr(state), packed.data_ptr(), loss.data_ptr(),
                                   grad.data_ptr(), ws.data_ptr(), ws.numel(), arr, world, int(rank), _ptr(epoch),
                                   SB_FIT_W_RESIDENT if w_resident else 0, _stream(dev)), "sb_fit_step")
+    if not w_resident:
+        bump_slot_generation(dev)
     return loss, grad, packed
 
 

@@ -298,16 +298,18 @@ def _train_adam_fused(train_loader, num_epochs, device, log_interval, save_inter
     if xi.dtype != torch.float32 or not xi.is_contiguous():
         raise ValueError('regressor.Xi must be a contiguous float32 parameter')
     state = native.fit_state(lib, xi.device)
-    resident = False
+    resident, gen = False, -1
     for epoch in range(num_epochs):
         mse_terms, loss_terms = [], []
         regressor.train()
         for x, dx in train_loader:
             x, dx = x.to(device), dx.to(device)
             n = x.reshape(-1, lib.dim).shape[0]
+            if native.slot_generation(xi.device) != gen:      # another fit has loaded the resident slot since
+                resident = False
             loss, _, packed = native.fit_step(x, dx, xi, regressor.mask, lib, 'adam', lr_sindy, w_mse=w_sindy_x,
                                               w_l1=w_sindy_reg, state=state, w_resident=resident)
-            resident = True
+            resident, gen = True, native.slot_generation(xi.device)
             mse_terms.append(packed[0] / (n * lib.dim))     # device scalars: no host sync inside the epoch
             loss_terms.append(loss.clone())
         if st_freq > 0 and (epoch + 1) % st_freq == 0:

@@ -70,16 +70,55 @@ def test_config3_lbfgs_with_symmreg_i_and_exp_library(golden, tmp_path):
 
 
 @needs_ref
-@pytest.mark.parametrize("key", ["C4", "C1w"])
-def test_wsindy_configs_through_the_dropin(key, golden, tmp_path):
-    """C4 `selkov/noise20_eq_wsindy.cfg` (w_sindy_reg = 0, T = 8000, cubic library, 50 test functions) and the dosc
-    weak-form cfg: main_wsindy.py -> WSINDyWrapper.solve on sb_wsindy_integrals. The goldens come from the reference on
-    the CPU, whose `torch.linalg.lstsq` is LAPACK gelsy (rank-revealing, rcond = eps*max(M, N)): SINDY_B200_LSTSQ=gelsy
-    selects that rank rule for the normal-equation solve (the default follows the CUDA driver `gels`: no truncation)."""
-    env = dict(ENV, SINDY_B200_LSTSQ="gelsy")
-    res, out = config_runs.run_entry(key, str(tmp_path), REF, dropin=True, gpu=0, env=env)
-    err = _compare(key, res, golden, 1e-4)
-    print(f"{key}: max coefficient error {err:.2e}")
+def test_wsindy_dosc_config_through_the_dropin(golden, tmp_path):
+    """`dosc/noise20_wsindy.cfg` through main_wsindy.py -> WSINDyWrapper.solve on sb_wsindy_integrals: a well-conditioned
+    weak-form fit; the reference's CPU run (fp32 gelsy), its float64 restatement and the drop-in (default driver) agree."""
+    res, _ = config_runs.run_entry("C1w", str(tmp_path), REF, dropin=True, gpu=0, env=ENV)
+    err = _compare("C1w", res, golden, 1e-4)
+    want64 = golden("configs")["C1w_f64_coefficients"]
+    assert np.abs(res["coefficients"] - want64).max() <= 1e-4 * np.abs(want64).max()
+    print(f"C1w: max coefficient error {err:.2e}")
+
+
+@needs_ref
+def test_config4_wsindy_selkov_through_the_dropin(golden, tmp_path):
+    """C4 `selkov/noise20_eq_wsindy.cfg` (w_sindy_reg = 0, T = 8000, cubic library, 50 test functions).
+
+    The reference's OWN result for this cfg is not reproducible: the stacked matrix [V'G; 0·I] has
+    sigma_min/sigma_max = 1.6e-4, LAPACK gelsy's fp32 rank decision (rcond = eps·8010 = 9.5e-4) sits on that edge, and
+    the run ends with dz0 ≡ 0 under OMP_NUM_THREADS=1, dz1 ≡ 0 under 8 threads, and two further different supports in
+    two default-thread runs — all stored in tests/golden/configs.npz (`C4_coefficients`,
+    `C4_reference_threads{1,8}_coefficients`) and checked below to DIFFER from each other. There is nothing to be
+    bit-compatible with, so the entry-point run is pinned to the well-defined object the fp32 call approximates: the same
+    STLSQ sequence with the least-squares solves in float64 (`oracle.wsindy_one_step(solve_dtype=float64)`, generated by
+    oracle/gen_config_golden.py from the same seed / trajectory / window): identical mask, coefficients to 1e-4.
+    The weak-form integrals themselves (G, b) are pinned to the reference at 1e-4 in test_gpu_parity::test_golden_wsindy,
+    and the gelsy rule is pinned on a reproducible rank-deficient case there (w0 sequence)."""
+    g = golden("configs")
+    runs = [g["C4_coefficients"], g["C4_reference_threads1_coefficients"], g["C4_reference_threads8_coefficients"]]
+    assert not np.array_equal(runs[1] != 0, runs[2] != 0), "the reference has become reproducible: pin C4 to it"
+    res, _ = config_runs.run_entry("C4", str(tmp_path), REF, dropin=True, gpu=0, env=ENV)
+    want = g["C4_f64_coefficients"]
+    got = res["coefficients"]
+    assert np.array_equal(got != 0, want != 0), f"C4: sparsity pattern differs\n{got}\n{want}"
+    err = np.abs(got - want).max() / np.abs(want).max()
+    assert err <= 1e-4, f"C4: coefficients differ by {err:.2e}\n{got}\n{want}"
+    print(f"C4: max coefficient error vs the float64 sequence {err:.2e}")
+
+
+@needs_ref
+@pytest.mark.parametrize("key,tol", [("C1", 2e-4), ("C2", 2e-4), ("C1w", 2e-4)])
+def test_live_against_the_reference_on_the_same_gpu(key, tol, tmp_path):
+    """The strongest drop-in statement available: the reference's entry point run TWICE on this B200, same seed —
+    once alone (`python baseline/_ref/main.py --gpu 0`: PyTorch-eager CUDA, initial Ξ from the CUDA generator) and once
+    through the launcher (this repo's sindy / model_utils / train / data_utils, same draws from the same generator).
+    Same mask, coefficients within 2e-4 of the largest (LBFGS stops at a parameter update of 1e-3, `train.py:643`)."""
+    a, _ = config_runs.run_entry(key, str(tmp_path / "ref"), REF, dropin=False, gpu=0)
+    b, _ = config_runs.run_entry(key, str(tmp_path / "b200"), REF, dropin=True, gpu=0)
+    assert np.array_equal(a["coefficients"] != 0, b["coefficients"] != 0), f"{a['coefficients']}\n{b['coefficients']}"
+    err = np.abs(a["coefficients"] - b["coefficients"]).max() / np.abs(a["coefficients"]).max()
+    assert err <= tol, f"{key}: {err:.2e}\n{a['coefficients']}\n{b['coefficients']}"
+    print(f"{key}: reference on cuda:0 vs drop-in on cuda:0: {err:.2e}")
 
 
 @needs_ref

@@ -251,3 +251,62 @@ def test_seed_sweep_recovers_the_damped_oscillator(capsys):
     agg = sweep.aggregate(res)
     assert agg["success_all"] == 4 and agg["rmse_all"][0] < 1e-3
     assert "Joint success rate = 4/4" in capsys.readouterr().out
+
+
+def test_fit_iterations_survive_foreign_calls_between_them():
+    """The one-launch iteration keeps Ξ⊙mask in the RESIDENT coefficient slot of the constant bank between launches. A
+    validation forward, a closure of another regressor, an STLSQ data pass or a second stepper running between two
+    iterations must not change a single bit of the fit (stateless calls use the scratch slot; another fit makes the
+    stepper re-pack through the slot generation)."""
+    from sindy_b200 import native
+    from sindy_b200.dist import FitStepper
+    lib = native.Library(3, 5)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    n = 300_001
+    x = torch.rand(n, 3, device="cuda", generator=g) * 2 - 1
+    dx = torch.randn(n, 3, device="cuda", generator=g)
+    Xi = torch.randn(3, 56, device="cuda", generator=g)
+    mask = (torch.rand(3, 56, device="cuda", generator=g) > 0.2).float()
+    other_W = torch.randn(3, 56, device="cuda", generator=g)
+
+    def run(disturb, use_graph):
+        st = FitStepper(lib, x, dx, "adam", lr=1e-2, w_l1=1e-3, use_graph=use_graph)
+        st.load(Xi, mask)
+        second = FitStepper(lib, x[:5000], dx[:5000], "sgd", lr=1e-3, use_graph=use_graph)
+        second.load(other_W, None)
+        losses = []
+        for it in range(6):
+            losses.append(st.step().clone())
+            if disturb:
+                native.forward(x[:4096], other_W, lib)                                   # validation forward
+                native.closure(x[:4096], dx[:4096], other_W, None, lib, 0.0)             # another regressor's closure
+                native.train_step(x[:4096], dx[:4096], other_W, lib, native.SB_STEP_LOSS | native.SB_STEP_GRAD)
+                second.step()                                                            # another fit on the device
+        return torch.stack(losses), st.xi.clone(), st.state.clone()
+
+    for use_graph in (False, True):
+        l0, xi0, s0 = run(False, use_graph)
+        l1, xi1, s1 = run(True, use_graph)
+        assert torch.equal(l0, l1) and torch.equal(xi0, xi1) and torch.equal(s0, s1), use_graph
+
+
+def test_stateless_calls_on_two_streams_do_not_race_on_the_scratch_slot():
+    """Closures with DIFFERENT coefficients issued back to back on two streams: the second waits for the first at the
+    scratch slot (event), so each sees its own W — same results as issuing them one after the other on one stream."""
+    from sindy_b200 import native
+    lib = native.Library(3, 5)
+    g = torch.Generator(device="cuda").manual_seed(6)
+    n = 2_000_000
+    x = torch.rand(n, 3, device="cuda", generator=g) * 2 - 1
+    dx = torch.randn(n, 3, device="cuda", generator=g)
+    Ws = [torch.randn(3, 56, device="cuda", generator=g) for _ in range(2)]
+    ref = [native.closure(x, dx, W, None, lib, 0.0)[0].clone() for W in Ws]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    for _ in range(5):
+        outs = []
+        for W, s in zip(Ws, streams):
+            with torch.cuda.stream(s):
+                outs.append(native.closure(x, dx, W, None, lib, 0.0)[0])
+        torch.cuda.synchronize()
+        assert torch.equal(outs[0], ref[0]) and torch.equal(outs[1], ref[1])

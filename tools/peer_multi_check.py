@@ -64,6 +64,21 @@ for (d, p) in ((3, 5), (2, 3)):
     if rank == 0:
         print(f"d={d} p={p}: vs nccl {e1:.1e}/{e2:.1e} vs single {e3:.1e}/{e4:.1e} ranks-bitwise-equal={same} repeat={rep} graph={gr} fit: ranks-equal={fit_same} loss {e5:.1e} xi {e6:.1e} -> {'OK' if good else 'FAIL'}")
 t = torch.tensor([1 if ok else 0], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MIN)
+# a lost peer: rank 0 launches one more iteration that nobody else joins. The kernel must give up after
+# $SB_PEER_TIMEOUT_MS, report NaN, leave the parameters / Adam state untouched and raise through FitStepper.check()
+lost_ok = True
 if rank == 0:
-    print("PEER TEST", "PASSED" if int(t) == 1 else "FAILED")
+    os.environ["SB_PEER_TIMEOUT_MS"] = "300"
+    xi_before, st_before = fit.xi.clone(), fit.state.clone()
+    fit._use_graph = False
+    l_lost = float(fit.step())
+    raised = False
+    try:
+        fit.check()
+    except native.SindyB200Error:
+        raised = True
+    lost_ok = (l_lost != l_lost) and torch.equal(fit.xi, xi_before) and torch.equal(fit.state, st_before) and raised
+    print(f"lost peer: loss={l_lost} parameters-untouched={torch.equal(fit.xi, xi_before)} check-raised={raised} -> {'OK' if lost_ok else 'FAIL'}")
+    print("PEER TEST", "PASSED" if (int(t) == 1 and lost_ok) else "FAILED")
+    torch.cuda.synchronize(); sys.stdout.flush(); os._exit(0 if (int(t) == 1 and lost_ok) else 1)
 torch.cuda.synchronize(); sys.stdout.flush(); os._exit(0 if int(t) == 1 else 1)
