@@ -755,6 +755,20 @@ def extras(native, dev, peaks, fp32_peak):
     out["stlsq_solve_SINDy_C5"] = {"samples_per_s": n / (ms * 1e-3), "ms": ms, "recovered_support_is_truth": support_ok,
                                    "max_coef_err_rel": coef_err}
     del x, dx, dxn
+    # WSINDy weak-form integrals over MANY trajectories: batches of Sel'kov-shaped trajectories
+    # (T = 8000, 50 test functions) for the config-4 library and for the C5 library; algorithmic cost per time sample
+    # (K−1−d) + 2·n_test·(K+d) flop (test functions are generated once per time tile for the whole batch) and 4·d bytes
+    for (dd, pp, ntr) in ((2, 3, 8192), (3, 5, 2048)):
+        wl = native.Library(dd, pp)
+        xt = torch.rand(ntr, 8000, dd, device=dev, generator=gen) * 0.8 + 0.2
+        ms = timed(lambda: native.wsindy_integrals(xt, wl, 0.002, 16.0, 50), reps=3)
+        fl = (wl.K - 1 - dd) + 2 * 50 * (wl.K + dd)
+        ns = ntr * 8000
+        out[f"wsindy_integrals_d{dd}_K{wl.K}_{ntr}traj_T8000"] = {
+            "samples_per_s": ns / (ms * 1e-3), "ms": ms, "flop_per_sample": fl, "bytes_per_sample": 4 * dd,
+            "fp32_tflops": fl * ns / (ms * 1e-3) / 1e12, "fp32_frac": fl * ns / (ms * 1e-3) / 1e12 / fp32_peak,
+            "hbm_gbs": 4 * dd * ns / (ms * 1e-3) / 1e9}
+        del xt
     x0 = torch.rand(10 ** 6, D, device=dev, generator=gen) * 2 - 1
     Xi = truth_xi(dev)
     ms = timed(lambda: native.rollout(x0, Xi, lib, 0.002, 2000, 10, "rk4"), reps=3)

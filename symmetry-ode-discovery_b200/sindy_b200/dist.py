@@ -306,9 +306,10 @@ class FitStepper:
         self._loaded = True
 
     def _own_slot(self):
-        """Before every launch / replay: if somebody else has loaded this stepper's slot since (only possible when more
-        than 7 steppers share a device), re-pack the coefficients — xi and mask live in this stepper's own memory."""
-        if native.slot_generation(self.x.device, self.w_slot) != self._slot_gen:
+        """Before every launch / replay: if another fit has loaded the device's resident coefficient slot since this
+        stepper did, re-pack — xi and mask live in this stepper's own memory. (Forward / closure / STLSQ calls use the
+        scratch slot and never cause this.)"""
+        if native.slot_generation(self.x.device) != self._slot_gen:
             self._slot_gen = native.load_w(self.xi, self.mask, self.lib)
 
     def check(self):

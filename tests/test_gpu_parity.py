@@ -385,6 +385,32 @@ def test_golden_wsindy(nat, golden):
     assert torch.equal(Gb[1], G0) and torch.equal(bb[1], b0)
 
 
+@pytest.mark.parametrize("d,p,n_traj,T,n_test", [(2, 3, 37, 1000, 50), (2, 2, 16, 333, 50), (3, 2, 9, 70, 7),
+                                                  (3, 3, 24, 2049, 64), (3, 5, 13, 1500, 50)])
+def test_wsindy_batched_kernel(nat, d, p, n_traj, T, n_test):
+    """WSINDy over many trajectories (SURVEY §8a a10 "at scale", §8e): the batched kernel (one CTA = a group of
+    trajectories, test functions generated once per time tile and shared, register-tiled contraction) against the CPU
+    oracle of `sindy.py:337-362` per trajectory and against the per-test-function kernel (taken below 8 trajectories).
+    Ragged sizes: trajectory counts that do not fill the last CTA, T that is not a multiple of the 64-sample tile nor
+    of the 1024-sample flush period, fewer than 64 test functions."""
+    lib = nat.Library(d, p)
+    rng = np.random.default_rng(100 * d + p)
+    dt = 0.002
+    t_max = T * dt
+    x = rng.uniform(0.2, 1.2, (n_traj, T, d)).astype(np.float32)
+    xd = torch.from_numpy(x).cuda()
+    G, b = nat.wsindy_integrals(xd, lib, dt, t_max, n_test)
+    assert G.shape == (n_traj, n_test, lib.K) and b.shape == (n_traj, n_test, d) and G.dtype == torch.float64
+    for r in (0, n_traj // 2, n_traj - 1):
+        Go, bo = O.wsindy_integrals(x[r], dt, t_max, p, n_test=n_test)
+        assert rel(G[r], Go) < 1e-4 and rel(b[r], bo) < 1e-4, (r, rel(G[r], Go), rel(b[r], bo))
+    Gs = torch.cat([nat.wsindy_integrals(xd[i:i + 5], lib, dt, t_max, n_test)[0] for i in range(0, n_traj, 5)])
+    bs = torch.cat([nat.wsindy_integrals(xd[i:i + 5], lib, dt, t_max, n_test)[1] for i in range(0, n_traj, 5)])
+    assert rel(G, Gs) < 1e-4 and rel(b, bs) < 1e-4, (rel(G, Gs), rel(b, bs))   # rotation recurrence vs per-sample sincosf
+    G2, b2 = nat.wsindy_integrals(xd, lib, dt, t_max, n_test)
+    assert torch.equal(G, G2) and torch.equal(b, b2)                      # deterministic
+
+
 # ---------------------------------------------------------------------------------------------------------
 # a11/a12: rollouts
 # ---------------------------------------------------------------------------------------------------------
