@@ -221,6 +221,29 @@ int sb_step_epilogue(const double* packed, const sb_library* lib, const float* x
  * "generic" ...). Static string. */
 const char* sb_train_step_variant(const sb_library* lib, uint32_t flags);
 
+/* Fused kernels of the symmetry regularisers (config 3, `lv/noise99_eq_isymreg.cfg`), for the libraries
+ * sb_symreg_supported() reports (d, poly_order, sin, exp) ∈ {(2,2,0,0), (2,2,0,1), (2,3,0,0), (3,2,0,0), (3,3,0,0)};
+ * other libraries: SB_ERR_UNSUPPORTED (the host side then composes sb_forward / sb_jvp / sb_jvp_backward through
+ * autograd like the reference composes its tensor ops).
+ *  - sb_euler_flow: fx = f(x), the flow map of n_steps explicit-Euler steps x ← x + dt·Θ(x)Wᵀ (`model_utils.py:236-240`
+ *    as called from `train.py:669-673`), and — when v is given — jv = J_f(x)·v (`model_utils.py:55-56`,
+ *    `jvp(f, x, v_x)[1]`), both (n × d) fp32, one launch.
+ *  - sb_euler_flow_backward: for cotangents g_fx, g_jv (either may be NULL) of those outputs: gw (d×K fp64) =
+ *    dL/dW, gv (n × d fp32, may be NULL) = dL/dv = J_f(x)ᵀ g_jv, gx (n × d, may be NULL) = dL/dx; one launch
+ *    (reverse sweep over the recomputed states, second derivatives of the library included). n_steps ≤ 32.
+ *  - sb_symreg_r: the reversed regulariser with precomputed group action (`model_utils.py:126-170`; gx = g(x) (n × d),
+ *    jgx = J_g(x) (n × d × d, row-major) as `precompute_symmreg_r` :172-211 provides them): out (fp64, d·K + 1) =
+ *    [Σ_n (J_g(x_n)ᵀ r_n)_i Θ_k(x_n) − r_{n,i} Θ_k(g(x_n))  (d×K) | Σ_n ‖r_n‖²],  r_n = J_g(x_n) h(x_n) − h(g(x_n)):
+ *    loss = out[d·K]/(n·d) and dL/dW = 2·out[:d·K]/(n·d) per group element, in one streaming pass. */
+int sb_symreg_supported(const sb_library* lib);
+int sb_euler_flow(const float* x, const float* v, int64_t n, const sb_library* lib, const float* w, float dt,
+                  int n_steps, float* fx, float* jv, void* stream);
+int sb_euler_flow_backward(const float* x, const float* v, const float* g_fx, const float* g_jv, int64_t n,
+                           const sb_library* lib, const float* w, float dt, int n_steps, double* gw, float* gv,
+                           float* gx, void* workspace, int64_t workspace_bytes, void* stream);
+int sb_symreg_r(const float* x, const float* gx, const float* jgx, int64_t n, const sb_library* lib, const float* w,
+                double* out, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* Fixed-step rollout of dx/dt = Θ(x)·Wᵀ for every initial condition in lock-step.
  *  - `model_utils.py:223-255` odeint (dtype SB_F32; method SB_EULER / SB_RK4; record_dx = 0):
  *      states after step s for s = stride, 2·stride, ... are written to x_out[(s/stride − 1), ic, :]

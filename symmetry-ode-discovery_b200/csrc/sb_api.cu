@@ -106,7 +106,9 @@ int64_t sb_workspace_bytes(const sb_library* lib) {
   if (s != SB_OK) return s;
   int64_t a = generic_workspace_bytes(t), b = fused_workspace_bytes(t), c = moments_workspace_bytes(t);
   if (b > a) a = b;
-  return c > a ? c : a;
+  if (c > a) a = c;
+  const int64_t e = symreg_workspace_bytes(t);
+  return e > a ? e : a;
 }
 
 int64_t sb_train_step_out_len(const sb_library* lib, uint32_t flags) {
@@ -396,6 +398,44 @@ int sb_wsindy_integrals(const float* x, int64_t n_traj, int64_t T, const sb_libr
   if (n_traj == 0) return SB_OK;
   SB_TRY(check_ptr(x, "x")); SB_TRY(check_ptr(G, "G")); SB_TRY(check_ptr(b, "b"));
   return wsindy_integrals(x, n_traj, T, t, dt, t_max, n_test, G, b, (cudaStream_t)stream);
+}
+
+int sb_symreg_supported(const sb_library* lib) {
+  LibTab t;
+  if (build_table(lib, &t) != SB_OK) return 0;
+  return symreg_supported(t) ? 1 : 0;
+}
+
+int sb_euler_flow(const float* x, const float* v, int64_t n, const sb_library* lib, const float* w, float dt,
+                  int n_steps, float* fx, float* jv, void* stream) {
+  LibTab t;
+  SB_TRY(build_table(lib, &t));
+  if (n < 0 || n_steps < 0) { set_error("bad sizes n=%lld n_steps=%d", (long long)n, n_steps); return SB_ERR_INVALID; }
+  if (n == 0) return SB_OK;
+  SB_TRY(check_ptr(x, "x")); SB_TRY(check_ptr(w, "w")); SB_TRY(check_ptr(fx, "fx"));
+  if (jv && !v) { set_error("jv requested without v"); return SB_ERR_INVALID; }
+  return euler_flow(x, v, n, t, w, dt, n_steps, fx, jv, (cudaStream_t)stream);
+}
+
+int sb_euler_flow_backward(const float* x, const float* v, const float* g_fx, const float* g_jv, int64_t n,
+                           const sb_library* lib, const float* w, float dt, int n_steps, double* gw, float* gv,
+                           float* gx, void* ws, int64_t ws_bytes, void* stream) {
+  LibTab t;
+  SB_TRY(build_table(lib, &t));
+  if (n < 0 || n_steps < 0) { set_error("bad sizes n=%lld n_steps=%d", (long long)n, n_steps); return SB_ERR_INVALID; }
+  SB_TRY(check_ptr(w, "w")); SB_TRY(check_ptr(gw, "gw")); SB_TRY(check_ptr(ws, "workspace"));
+  if (n > 0) SB_TRY(check_ptr(x, "x"));
+  return euler_flow_backward(x, v, g_fx, g_jv, n, t, w, dt, n_steps, gw, gv, gx, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int sb_symreg_r(const float* x, const float* gx, const float* jgx, int64_t n, const sb_library* lib, const float* w,
+                double* out, void* ws, int64_t ws_bytes, void* stream) {
+  LibTab t;
+  SB_TRY(build_table(lib, &t));
+  if (n < 0) { set_error("bad size n=%lld", (long long)n); return SB_ERR_INVALID; }
+  SB_TRY(check_ptr(w, "w")); SB_TRY(check_ptr(out, "out")); SB_TRY(check_ptr(ws, "workspace"));
+  if (n > 0) { SB_TRY(check_ptr(x, "x")); SB_TRY(check_ptr(gx, "gx")); SB_TRY(check_ptr(jgx, "jgx")); }
+  return symreg_r(x, gx, jgx, n, t, w, out, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 void sb_debug_trace(void* dev_buf) { fused_set_trace(reinterpret_cast<unsigned long long*>(dev_buf)); }

@@ -264,6 +264,17 @@ int rollout(const void* x0, int64_t n_ics, const LibTab& t, const void* w, doubl
 int wsindy_integrals(const float* x, int64_t n_traj, int64_t T, const LibTab& t, float dt, double t_max,
                      int n_test, double* G, double* b, cudaStream_t s);
 
+// fused symmetry-regulariser kernels (sb_symreg.cu): Euler flow map with JVP and its reverse sweep, reversed regulariser
+bool symreg_supported(const LibTab& t);
+int64_t symreg_workspace_bytes(const LibTab& t);
+int euler_flow(const float* x, const float* v, int64_t n, const LibTab& t, const float* w, float dt, int n_steps,
+               float* fx, float* jv, cudaStream_t s);
+int euler_flow_backward(const float* x, const float* v, const float* g_fx, const float* g_jv, int64_t n,
+                        const LibTab& t, const float* w, float dt, int n_steps, double* gw, float* gv, float* gx,
+                        void* ws, int64_t ws_bytes, cudaStream_t s);
+int symreg_r(const float* x, const float* gx, const float* jg, int64_t n, const LibTab& t, const float* w,
+             double* out, void* ws, int64_t ws_bytes, cudaStream_t s);
+
 // FP32 peak microbenchmark
 int fp32_peak(int variant, int iters, double* tflops_host, cudaStream_t s);
 

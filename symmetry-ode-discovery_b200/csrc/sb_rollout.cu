@@ -38,17 +38,24 @@ template <> __device__ __forceinline__ float div_rn<float>(float a, float b) { r
 template <> __device__ __forceinline__ double div_rn<double>(double a, double b) { return __ddiv_rn(a, b); }
 
 // ---- right-hand sides ---------------------------------------------------------------------------
-// specialised: compile-time polynomial library, W from the constant bank
-template <int D, int P, class T>
+// specialised: compile-time library (polynomial block + optional sin / exp columns), W from the constant bank
+template <int D, int P, class T, int S = 0, int E = 0>
 struct SpecRhs {
   static constexpr int DN = D;
   __device__ __forceinline__ int dim() const { return D; }
   // `off` (always 0, opaque, different per call site) only matters in fp64: it keeps ptxas from hoisting coefficient
   // loads out of the time loop into registers it does not have (168 registers + spills -> 136, none)
   __device__ __forceinline__ void eval(const T (&x)[D], T (&f)[D], int off = 0) const {
-    constexpr int K = Poly<D, P>::K;
+    constexpr int NP = Poly<D, P>::K;
+    constexpr int K = NP + D * (S + E);
     T m[K];
-    expand_poly<D, P>(x, m);
+    {
+      T mp[NP];
+      expand_poly<D, P>(x, mp);
+      static_for<0, NP>([&](auto k) { m[k] = mp[k]; });
+      if constexpr (S) static_for<0, D>([&](auto j) { m[NP + j] = sin(x[j]); });          // sinf / sin by overload
+      if constexpr (E) static_for<0, D>([&](auto j) { m[NP + D * S + j] = exp(x[j]); });
+    }
     if constexpr (std::is_same<T, float>::value && K % 2 == 0) {
       // fp32: packed fma.rn.f32x2 over adjacent columns, W pairs straight from the constant bank
       const float2* w2 = reinterpret_cast<const float2*>(c_rw);
@@ -217,10 +224,10 @@ __device__ __forceinline__ void rollout_body(const RHS& rhs, const RollArgs& a) 
   }
 }
 
-template <int D, int P, class T>
+template <int D, int P, class T, int S = 0, int E = 0>
 __global__ void __launch_bounds__(kThreads) rollout_spec_kernel(RollArgs a) {
-  SpecRhs<D, P, T> rhs;
-  rollout_body<SpecRhs<D, P, T>, T>(rhs, a);
+  SpecRhs<D, P, T, S, E> rhs;
+  rollout_body<SpecRhs<D, P, T, S, E>, T>(rhs, a);
 }
 
 template <class T, int KMAX>
@@ -278,8 +285,15 @@ __device__ __forceinline__ void eval_multi(const float (&x)[NB][D], float (&f)[N
   });
 }
 
+// Blocks of kMultiThreads = 64 threads (128 initial conditions): with the whole batch resident at once — 1e6 / 8 ICs per
+// GPU in the sharded C5 rollout is two thirds of one wave — the SM loads differ by at most one block, and the run time is
+// set by the fullest SM: 128-thread blocks gave 489 blocks over 148 SMs = 3 or 4 per SM (+21 % on the slowest, measured
+// as 6.58x at 8 GPUs instead of 8x); 64-thread blocks give 6 or 7.
+constexpr int kMultiThreads = 64;
+
 template <int D, int P, int NB>
-__global__ void __launch_bounds__(kThreads) rollout_rk4_multi_kernel(RollArgs a) {
+__global__ void __launch_bounds__(kMultiThreads) rollout_rk4_multi_kernel(RollArgs a) {
+  constexpr int kThreads = kMultiThreads;
   const int64_t base = (int64_t)blockIdx.x * (kThreads * NB) + threadIdx.x;
   if (base >= a.n_ics) return;
   const float* x0 = reinterpret_cast<const float*>(a.x0);
@@ -350,8 +364,8 @@ int launch_rollout(const LibTab& t, const void* w, const RollArgs& a, cudaStream
     SB_CUDA_TRY(cudaMemcpyToSymbolAsync(c_rw, w, sizeof(T) * D * Poly<D, P>::K, 0, cudaMemcpyDeviceToDevice, s)); \
     if constexpr (std::is_same<T, float>::value && Poly<D, P>::K % 2 == 0) {                                   \
       if (a.method == SB_RK4 && !a.record_dx && rollout_multi_enabled()) {                                     \
-        const unsigned g2 = (unsigned)((a.n_ics + 2 * kThreads - 1) / (2 * kThreads));                         \
-        rollout_rk4_multi_kernel<D, P, 2><<<g2, kThreads, 0, s>>>(a);                                          \
+        const unsigned g2 = (unsigned)((a.n_ics + 2 * kMultiThreads - 1) / (2 * kMultiThreads));               \
+        rollout_rk4_multi_kernel<D, P, 2><<<g2, kMultiThreads, 0, s>>>(a);                                     \
         SB_LAUNCH_CHECK("rollout_rk4_multi_kernel");                                                           \
         return SB_OK;                                                                                          \
       }                                                                                                        \
@@ -362,6 +376,13 @@ int launch_rollout(const LibTab& t, const void* w, const RollArgs& a, cudaStream
   }
     SB_ROLL_SHAPES(X)
 #undef X
+  }
+  // Lotka-Volterra in canonical coordinates (`data_utils/lotka.py:33-41`; config 3's library): (2, 2) + exp, K = 8
+  if (t.d == 2 && t.n_poly == n_poly_terms(2, 2) && !t.sine && t.exp_) {
+    SB_CUDA_TRY(cudaMemcpyToSymbolAsync(c_rw, w, sizeof(T) * 2 * 8, 0, cudaMemcpyDeviceToDevice, s));
+    rollout_spec_kernel<2, 2, T, 0, 1><<<grid, kThreads, 0, s>>>(a);
+    SB_LAUNCH_CHECK("rollout_spec_kernel");
+    return SB_OK;
   }
   if (t.K <= 16) rollout_gen_kernel<T, 16><<<grid, kThreads, 0, s>>>(t, reinterpret_cast<const T*>(w), a);
   else if (t.K <= 64) rollout_gen_kernel<T, 64><<<grid, kThreads, 0, s>>>(t, reinterpret_cast<const T*>(w), a);

@@ -15,10 +15,11 @@ from functools import partial
 import torch
 from torch.autograd.functional import jvp
 
-from sindy_b200 import native
+from sindy_b200 import native, ops
 
 __all__ = [
-    "symmreg_i", "symmreg_f", "symmreg_r", "symmreg_r_precomputed", "precompute_symmreg_r", "odeint",
+    "symmreg_i", "symmreg_f", "symmreg_r", "symmreg_r_precomputed", "precompute_symmreg_r", "odeint", "EulerFlowMap",
+    "group_action_and_jacobian",
     "make_symmreg", "make_symmreg_pttrain", "make_symmreg_np", "make_fsymmreg", "make_fsymmreg_pttrain",
     "make_fsymmreg_np", "make_rsymmreg", "make_rsymmreg_pttrain",
 ]
@@ -26,6 +27,42 @@ __all__ = [
 
 def _jvp_fn(require_grad):
     return partial(jvp, create_graph=True, strict=True) if require_grad else jvp
+
+
+def _is_regressor(f):
+    return hasattr(f, 'library') and hasattr(f, 'mask') and hasattr(f, '_current_Xi')
+
+
+class EulerFlowMap:
+    """f(x) = odeint(regressor, x, t, dt) with method 'euler' — the flow map `train.py:669-673` builds as a local
+    closure — as an object that ALSO knows its Jacobian-vector product: `jvp(x, v)` returns (f(x), J_f(x)·v) from ONE
+    kernel launch (sb_euler_flow) with a one-launch backward, where the reference runs two reverse passes through
+    n Python Euler steps with create_graph=True (`model_utils.py:55-56`). `symmreg_i` uses it when it is handed one;
+    any other callable takes the reference's double-vjp path. Falls back to the operator-by-operator composition for
+    libraries without a fused kernel or off the GPU."""
+
+    def __init__(self, regressor, t, dt):
+        self.regressor, self.t, self.dt = regressor, t, dt
+        self.n_steps = int(t / dt)
+
+    def _fused(self, x):
+        return (_is_regressor(self.regressor) and torch.is_tensor(x) and x.is_cuda
+                and native.symreg_supported(self.regressor.library))
+
+    def _w(self):
+        reg = self.regressor
+        reg.Xi = reg._current_Xi()
+        return reg.Xi * reg.mask
+
+    def __call__(self, x):
+        if self._fused(x) and not (torch.is_grad_enabled() and x.requires_grad):
+            return ops.euler_flow(x, None, self._w(), self.regressor.library, self.dt, self.n_steps)[0]
+        return odeint(self.regressor, x, self.t, self.dt)
+
+    def jvp(self, x, v, require_grad=True):
+        if self._fused(x) and not (torch.is_grad_enabled() and x.requires_grad):
+            return ops.euler_flow(x, v, self._w(), self.regressor.library, self.dt, self.n_steps)
+        return _jvp_fn(require_grad)(lambda q: odeint(self.regressor, q, self.t, self.dt), x, v)
 
 
 def _centred_latent(autoencoder, x, normalize, z_mean):
@@ -75,7 +112,9 @@ def symmreg_i(x_fx, autoencoder, generator, f=None, dfdx=None, normalize='global
         for v in generator.get_full_basis_list():
             tangent = jvp_fn(autoencoder.decoder, z, v=_act_on_latent(v, z))[1]
             v_x, v_fx = tangent[:, 0], tangent[:, 1]
-            if f is not None:
+            if isinstance(f, EulerFlowMap):
+                pushed = f.jvp(x, v_x, require_grad)[1]          # one fused launch instead of a double vjp
+            elif f is not None:
                 pushed = jvp_fn(f, x, v_x)[1]
             else:
                 pushed = torch.einsum('bjk,bk->bj', dfdx, v_x)
@@ -138,14 +177,47 @@ def symmreg_r(x, autoencoder, generator, h, normalize='global', z_mean=None, req
 
 
 def symmreg_r_precomputed(x, gx_list, Jgx_list, h):
-    '''symmreg_r with g(x) and J_g(x) from precompute_symmreg_r: a pure streaming loss in the SINDy operators
-    (two library evaluations and one d×d mat-vec per sample and group element).'''
+    '''symmreg_r with g(x) and J_g(x) precomputed (they do not depend on Ξ): a pure streaming loss — two library
+    evaluations and one d×d mat-vec per sample and group element. When `h` is a SINDyRegression on the GPU with a fused
+    kernel (sb_symreg_r) value AND dL/dΞ come from ONE launch per group element; otherwise composed from h(x), h(g(x)).'''
     loss = 0.0
+    fused = (_is_regressor(h) and x.is_cuda and native.symreg_supported(h.library)
+             and not (torch.is_grad_enabled() and x.requires_grad))
+    if fused:
+        h.Xi = h._current_Xi()
+        w = h.Xi * h.mask
     for gx, Jgx in zip(gx_list, Jgx_list):
         d = x.shape[-1]
+        if fused:
+            loss = loss + ops.symreg_r_loss(x, gx, Jgx.reshape(-1, d, d), w, h.library)
+            continue
         pushed = torch.einsum('bij,bj->bi', Jgx.reshape(-1, d, d), h(x))  # the reference's Jgx is (B, 1, d, d)
         loss = loss + torch.mean((pushed - h(gx)) ** 2)
     return loss
+
+
+def group_action_and_jacobian(x, autoencoder, generator, z_mean=None, scale=0.01, normalize='global'):
+    '''g(x) and the TRUE Jacobian J_g(x) (B, d, d) of every deterministic group element, as `symmreg_r` uses them
+    (`model_utils.py:145-163`: `jvp(group_transform, x, v=h(x))`): column j of J_g is the JVP with the j-th unit vector.
+    They do not depend on Ξ, so a fit computes them ONCE and evaluates `symmreg_r_precomputed` in every closure — the
+    autoencoder leaves the closure entirely. (`precompute_symmreg_r` keeps the reference's own `vmap(jacfwd)` result,
+    which stacks on the wrong axis; this is the quantity the loss `symmreg_r` actually contracts with.)'''
+    autoencoder.eval()
+    generator.eval()
+    gx_list, Jgx_list = [], []
+    d = x.shape[-1]
+    with torch.no_grad():
+        for g in generator.get_deterministic_group_elems(scale=scale):
+            move = partial(_group_transform, autoencoder, g, normalize=normalize, z_mean=z_mean)
+            gx_list.append(move(x))
+            cols = []
+            for j in range(d):
+                e = torch.zeros_like(x)
+                e[:, j] = 1.0
+                with torch.enable_grad():
+                    cols.append(jvp(move, x, v=e)[1].detach())
+            Jgx_list.append(torch.stack(cols, dim=-1))            # [b, a, j] = d g_a / d x_j
+    return gx_list, Jgx_list
 
 
 def precompute_symmreg_r(x, autoencoder, generator, z_mean=None, scale=0.01):

@@ -72,6 +72,13 @@ _SIGNATURES = {
                            c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sb_wsindy_integrals": (c_int, [c_void_p, c_int64, c_int64, POINTER(_CLibrary), c_float, c_double, c_int,
                                     c_void_p, c_void_p, c_void_p]),
+    "sb_symreg_supported": (c_int, [POINTER(_CLibrary)]),
+    "sb_euler_flow": (c_int, [c_void_p, c_void_p, c_int64, POINTER(_CLibrary), c_void_p, c_float, c_int, c_void_p,
+                              c_void_p, c_void_p]),
+    "sb_euler_flow_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, POINTER(_CLibrary), c_void_p,
+                                       c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "sb_symreg_r": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, POINTER(_CLibrary), c_void_p, c_void_p, c_void_p,
+                            c_int64, c_void_p]),
     "sb_debug_trace": (None, [c_void_p]),
     "sb_fp32_peak": (c_int, [c_int, c_int, POINTER(c_double), c_void_p]),
 }
@@ -527,6 +534,65 @@ def wsindy_integrals(x: torch.Tensor, lib: Library, dt: float, t_max: float, n_t
                                           int(n_test), G.data_ptr(), b.data_ptr(), _stream(dev)),
                "sb_wsindy_integrals")
     return (G[0], b[0]) if single else (G, b)
+
+
+def symreg_supported(lib: Library) -> bool:
+    """True if the fused Euler-flow / reversed-regulariser kernels exist for this library."""
+    return bool(load().sb_symreg_supported(ctypes.byref(lib.c())))
+
+
+def euler_flow(x: torch.Tensor, v: Optional[torch.Tensor], w: torch.Tensor, lib: Library, dt: float, n_steps: int):
+    """fx = n_steps explicit-Euler steps of h(x) = Θ(x)Wᵀ from x (`model_utils.py:236-240`) and, with v, jv = J_f(x)·v
+    (`model_utils.py:55-56`), one launch. Shapes of x are kept; returns (fx, jv or None)."""
+    xf = _flat(_f32c(x, "x"), lib.dim, "x")
+    vf = _flat(_f32c(v, "v"), lib.dim, "v") if v is not None else None
+    wf = _f32c(w, "w")
+    fx = torch.empty_like(xf)
+    jv = torch.empty_like(xf) if vf is not None else None
+    with torch.cuda.device(xf.device):
+        _check(load().sb_euler_flow(xf.data_ptr(), _ptr(vf), xf.shape[0], ctypes.byref(lib.c()), wf.data_ptr(),
+                                    float(dt), int(n_steps), fx.data_ptr(), _ptr(jv), _stream(xf.device)),
+               "sb_euler_flow")
+    return fx.view(x.shape), (jv.view(x.shape) if jv is not None else None)
+
+
+def euler_flow_backward(x, v, g_fx, g_jv, w, lib: Library, dt: float, n_steps: int, need_gv=True, need_gx=False):
+    """Reverse sweep of euler_flow: (gw (d×K fp64), gv or None, gx or None) for cotangents g_fx / g_jv (either None)."""
+    xf = _flat(_f32c(x, "x"), lib.dim, "x")
+    vf = _flat(_f32c(v, "v"), lib.dim, "v") if v is not None else None
+    gf = _flat(_f32c(g_fx, "g_fx"), lib.dim, "g_fx") if g_fx is not None else None
+    gj = _flat(_f32c(g_jv, "g_jv"), lib.dim, "g_jv") if g_jv is not None else None
+    wf = _f32c(w, "w")
+    dev = xf.device
+    gw = torch.empty(lib.dim, lib.K, dtype=torch.float64, device=dev)
+    gv = torch.empty_like(xf) if (need_gv and vf is not None) else None
+    gx = torch.empty_like(xf) if need_gx else None
+    ws = _workspace(lib, dev)
+    with torch.cuda.device(dev):
+        _check(load().sb_euler_flow_backward(xf.data_ptr(), _ptr(vf), _ptr(gf), _ptr(gj), xf.shape[0],
+                                             ctypes.byref(lib.c()), wf.data_ptr(), float(dt), int(n_steps),
+                                             gw.data_ptr(), _ptr(gv), _ptr(gx), ws.data_ptr(), ws.numel(),
+                                             _stream(dev)), "sb_euler_flow_backward")
+    return gw, (gv.view(x.shape) if gv is not None else None), (gx.view(x.shape) if gx is not None else None)
+
+
+def symreg_r(x: torch.Tensor, gx: torch.Tensor, jgx: torch.Tensor, w: torch.Tensor, lib: Library) -> torch.Tensor:
+    """Packed fp64 sums of the reversed regulariser for one group element: out[:d·K] = gradient sums (d×K), out[d·K] =
+    Σ‖J_g(x)h(x) − h(g(x))‖² (`model_utils.py:126-170`); one streaming launch."""
+    xf = _flat(_f32c(x, "x"), lib.dim, "x")
+    gf = _flat(_f32c(gx, "gx"), lib.dim, "gx")
+    jf = _f32c(jgx, "jgx").reshape(-1, lib.dim, lib.dim)
+    if gf.shape[0] != xf.shape[0] or jf.shape[0] != xf.shape[0]:
+        raise ValueError("x, gx and jgx must describe the same samples")
+    wf = _f32c(w, "w")
+    dev = xf.device
+    out = torch.empty(lib.dim * lib.K + 1, dtype=torch.float64, device=dev)
+    ws = _workspace(lib, dev)
+    with torch.cuda.device(dev):
+        _check(load().sb_symreg_r(xf.data_ptr(), gf.data_ptr(), jf.data_ptr(), xf.shape[0], ctypes.byref(lib.c()),
+                                  wf.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev)),
+               "sb_symreg_r")
+    return out
 
 
 def fp32_peak(variant: int = 1, iters: int = 4096, device: Optional[torch.device] = None) -> float:

@@ -163,5 +163,85 @@ class _FusedMSE(Function):
 
 
 def fused_mse(x: torch.Tensor, dx: torch.Tensor, w: torch.Tensor, lib: Library) -> torch.Tensor:
-    """One-pass MSE loss whose backward (w.r.t. W only) costs nothing extra."""
+    """One-pass MSE loss whose backward (w.r.t. W only) costs nothing extra. The fused pass differentiates with respect
+    to the PARAMETERS only: if x or dx carry a gradient (a latent z / dz from an encoder being trained) the loss is
+    composed from the differentiable forward operator instead, so that no gradient is silently dropped."""
+    if torch.is_grad_enabled() and (x.requires_grad or dx.requires_grad):
+        return torch.nn.functional.mse_loss(sindy_forward(x, w, lib), dx)
     return _FusedMSE.apply(x, dx, w, lib)
+
+
+class _EulerFlow(Function):
+    """(fx, jv) = (f(x), J_f(x)·v) for the flow map f of n explicit-Euler steps of h (`model_utils.py:236-240, 55-56`):
+    one launch forward, one launch backward (gradients w.r.t. v, W and — if asked — x). Once differentiable: the
+    reference needs second order only because it builds the JVP itself by a double vjp."""
+
+    @staticmethod
+    def forward(ctx, x, v, w, lib: Library, dt: float, n_steps: int):
+        ctx.meta = (lib, float(dt), int(n_steps))
+        ctx.save_for_backward(x, v, w)
+        fx, jv = native.euler_flow(x, v, w, lib, dt, n_steps)
+        return fx, jv
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_fx, g_jv):
+        x, v, w = ctx.saved_tensors
+        lib, dt, n_steps = ctx.meta
+        gw, gv, gx = native.euler_flow_backward(x, v, g_fx, g_jv, w, lib, dt, n_steps, need_gv=_rg(ctx, 1),
+                                                need_gx=_rg(ctx, 0))
+        return gx, gv, (gw.to(w.dtype) if _rg(ctx, 2) else None), None, None, None
+
+
+class _EulerFlowValue(Function):
+    """fx = f(x) alone (no tangent)."""
+
+    @staticmethod
+    def forward(ctx, x, w, lib: Library, dt: float, n_steps: int):
+        ctx.meta = (lib, float(dt), int(n_steps))
+        ctx.save_for_backward(x, w)
+        return native.euler_flow(x, None, w, lib, dt, n_steps)[0]
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_fx):
+        x, w = ctx.saved_tensors
+        lib, dt, n_steps = ctx.meta
+        gw, _, gx = native.euler_flow_backward(x, None, g_fx, None, w, lib, dt, n_steps, need_gv=False,
+                                               need_gx=_rg(ctx, 0))
+        return gx, (gw.to(w.dtype) if _rg(ctx, 1) else None), None, None, None
+
+
+def euler_flow(x, v, w, lib: Library, dt: float, n_steps: int):
+    """Differentiable (f(x), J_f(x)·v) — v may be None: (f(x), None)."""
+    if v is None:
+        return _EulerFlowValue.apply(x, w, lib, dt, n_steps), None
+    return _EulerFlow.apply(x, v, w, lib, dt, n_steps)
+
+
+class _SymregR(Function):
+    """mean((J_g(x)h(x) − h(g(x)))²) for one group element with precomputed g(x), J_g(x): value and dL/dW from ONE
+    streaming pass (`model_utils.py:126-170`)."""
+
+    @staticmethod
+    def forward(ctx, x, gx, jgx, w, lib: Library):
+        out = native.symreg_r(x, gx, jgx, w, lib)
+        n = x.numel() // lib.dim
+        denom = float(max(n, 1) * lib.dim)
+        ctx.save_for_backward(out)
+        ctx.meta = (lib, denom, w.dtype)
+        return (out[lib.dim * lib.K] / denom).to(torch.float32)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gl):
+        (out,) = ctx.saved_tensors
+        lib, denom, wdtype = ctx.meta
+        gw = None
+        if ctx.needs_input_grad[3]:
+            gw = (out[:lib.dim * lib.K].view(lib.dim, lib.K) * (2.0 / denom) * gl.double()).to(wdtype)
+        return None, None, None, gw, None
+
+
+def symreg_r_loss(x, gx, jgx, w, lib: Library) -> torch.Tensor:
+    return _SymregR.apply(x, gx, jgx, w, lib)

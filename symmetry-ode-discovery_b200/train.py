@@ -18,7 +18,8 @@ from copy import deepcopy
 import numpy as np
 import torch
 
-from model_utils import make_fsymmreg_pttrain, make_rsymmreg_pttrain, make_symmreg_pttrain, odeint
+from model_utils import (EulerFlowMap, group_action_and_jacobian, make_fsymmreg_pttrain, make_rsymmreg_pttrain,
+                         make_symmreg_pttrain, odeint, symmreg_r_precomputed)
 from sindy import solve_SINDy_one_step
 
 __all__ = ["train_SIGED_lbfgs", "train_SIGED", "train_WSINDy", "train_SINDy"]
@@ -161,6 +162,9 @@ def train_SIGED_lbfgs(
     stats = None
     if kwargs.get('cached_gram') and not use_latent:
         stats = regressor.sufficient_statistics(x, dx)
+    group_cache = None
+    if w_sym_reg > 0.0 and sym_reg_type == 'r' and not use_latent and kwargs.get('precompute_group', True):
+        group_cache = group_action_and_jacobian(x, autoencoder, generator)
 
     def data_loss(losses):
         if use_latent:
@@ -179,10 +183,15 @@ def train_SIGED_lbfgs(
         loss = w_sindy_x * loss_x
         if w_sym_reg > 0.0:
             if sym_reg_type in ('i', 'f'):
-                def forward_step(q):
-                    return odeint(regressor, q, int_t, int_dt)
+                # the flow map of `train.py:669-673` as an object that knows its own JVP: symmreg_i then takes
+                # (f(x), J_f(x)·v) from one fused launch instead of a double vjp through the Euler steps
+                forward_step = EulerFlowMap(regressor, int_t, int_dt)
                 x_fx = torch.stack([x, forward_step(x)], dim=1)
                 loss_sym = symm_loss(x_fx, f=forward_step)
+            elif group_cache:
+                # g(x), J_g(x) do not depend on Ξ: formed once for the (fixed) batch, then one streaming launch per
+                # group element and closure (`model_utils.py:126-170`)
+                loss_sym = symmreg_r_precomputed(x, group_cache[0], group_cache[1], regressor)
             else:
                 loss_sym = symm_loss(x, h=regressor)
             losses['loss_sym_reg'] = loss_sym.detach()

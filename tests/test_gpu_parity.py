@@ -541,6 +541,80 @@ def test_golden_symmreg(nat, golden):
         gx_list, Jgx_list = model_utils.precompute_symmreg_r(x, ae, gen)
         assert rel(torch.stack(gx_list), g[tag + "_gx"]) < 1e-5
         assert rel(torch.stack(Jgx_list), g[tag + "_Jgx_ref"]) < 1e-4
+        # the fused sym-reg kernels: the flow map as an object that knows its JVP (one launch forward, one backward) in
+        # place of the closure + double vjp, against the SAME golden of the reference's symmreg_i
+        flow = model_utils.EulerFlowMap(reg, 0.1, 0.01)
+        assert nat.symreg_supported(reg.library)
+        x_fx = torch.stack([x, flow(x)], dim=1)
+        li = model_utils.symmreg_i(x_fx, ae, gen, f=flow, require_grad=True)
+        reg.zero_grad(); li.backward()
+        assert abs(float(li) - float(g[tag + "_li"])) < 1e-4 * float(g[tag + "_li"])
+        assert rel(reg.Xi.grad, g[tag + "_gi"]) < 5e-4
+        # g(x) and the TRUE J_g(x) computed once per fit, then the streaming kernel per closure == symmreg_r
+        gx2, Jgx2 = model_utils.group_action_and_jacobian(x, ae, gen)
+        assert rel(torch.stack(gx2), g[tag + "_gx"]) < 1e-5 and rel(torch.stack(Jgx2), g[tag + "_Jgx"]) < 1e-4
+        reg.zero_grad()
+        lp = model_utils.symmreg_r_precomputed(x, gx2, Jgx2, reg)
+        lp.backward()
+        assert abs(float(lp) - float(g[tag + "_lr"])) < 1e-4 * float(g[tag + "_lr"])
+        assert rel(reg.Xi.grad, g[tag + "_gr"]) < 5e-4
+
+
+@pytest.mark.parametrize("d,p,e", [(2, 2, 1), (2, 2, 0), (2, 3, 0), (3, 2, 0), (3, 3, 0)])
+def test_fused_euler_flow_and_reversed_regulariser_vs_composition(nat, d, p, e):
+    """sb_euler_flow / sb_euler_flow_backward / sb_symreg_r against the operator-by-operator composition the reference's
+    code performs (Python Euler steps of the differentiable forward operator, `torch.autograd.functional.jvp` with
+    create_graph=True, einsum): values 1e-5, gradients w.r.t. W, v and x 1e-4 (relative to the largest entry)."""
+    import model_utils
+    from sindy_b200 import ops
+    from torch.autograd.functional import jvp
+    lib = nat.Library(d, p, False, bool(e))
+    gen = torch.Generator(device="cuda").manual_seed(10 * d + p + e)
+    n = 3001
+    x = torch.rand(n, d, device="cuda", generator=gen) * 1.2 - 0.6
+    v = torch.randn(n, d, device="cuda", generator=gen)
+    W0 = 0.3 * torch.randn(d, lib.K, device="cuda", generator=gen)
+    a = torch.randn(n, d, device="cuda", generator=gen)
+    b = torch.randn(n, d, device="cuda", generator=gen)
+    dt, steps = 0.01, 10
+
+    def flow_ref(q, W):
+        for _ in range(steps):
+            q = q + dt * ops.sindy_forward(q, W, lib)
+        return q
+
+    W = W0.clone().requires_grad_(True)
+    vr = v.clone().requires_grad_(True)
+    xr = x.clone().requires_grad_(True)
+    fx_r, jv_r = jvp(lambda q: flow_ref(q, W), xr, vr, create_graph=True)
+    (gW_r, gv_r, gx_r) = torch.autograd.grad((fx_r * a).sum() + (jv_r * b).sum(), (W, vr, xr))
+
+    W2 = W0.clone().requires_grad_(True)
+    v2 = v.clone().requires_grad_(True)
+    x2 = x.clone().requires_grad_(True)
+    fx, jv = ops.euler_flow(x2, v2, W2, lib, dt, steps)
+    assert rel(fx, fx_r) < 1e-5 and rel(jv, jv_r) < 1e-5, (rel(fx, fx_r), rel(jv, jv_r))
+    gW, gv, gx = torch.autograd.grad((fx * a).sum() + (jv * b).sum(), (W2, v2, x2))
+    assert rel(gW, gW_r) < 1e-4 and rel(gv, gv_r) < 1e-4 and rel(gx, gx_r) < 1e-4, (rel(gW, gW_r), rel(gv, gv_r), rel(gx, gx_r))
+    fx_only, none = ops.euler_flow(x, None, W2, lib, dt, steps)
+    assert none is None and rel(fx_only, fx_r) < 1e-5
+    (gW1,) = torch.autograd.grad((fx_only * a).sum(), (W2,))
+    (gW1_r,) = torch.autograd.grad((flow_ref(x, W) * a).sum(), (W,))
+    assert rel(gW1, gW1_r) < 1e-4
+    # reversed regulariser
+    gx_pts = x + 0.05 * torch.randn(n, d, device="cuda", generator=gen)
+    J = torch.eye(d, device="cuda").expand(n, d, d) + 0.1 * torch.randn(n, d, d, device="cuda", generator=gen)
+    W3 = W0.clone().requires_grad_(True)
+    l_f = ops.symreg_r_loss(x, gx_pts, J.contiguous(), W3, lib)
+    (g_f,) = torch.autograd.grad(l_f, (W3,))
+    W4 = W0.clone().requires_grad_(True)
+    pushed = torch.einsum('bij,bj->bi', J, ops.sindy_forward(x, W4, lib))
+    l_r = torch.mean((pushed - ops.sindy_forward(gx_pts, W4, lib)) ** 2)
+    (g_r,) = torch.autograd.grad(l_r, (W4,))
+    assert abs(float(l_f) - float(l_r)) < 1e-5 * abs(float(l_r)) and rel(g_f, g_r) < 1e-4, (float(l_f), float(l_r), rel(g_f, g_r))
+    want = O.symmreg_r_precomputed(x.cpu().numpy(), [gx_pts.cpu().numpy()], [J.cpu().numpy()], W0.cpu().numpy(), p,
+                                   False, bool(e))
+    assert abs(float(l_f) - float(want)) < 1e-5 * abs(float(want))
 
 
 # ---------------------------------------------------------------------------------------------------------
