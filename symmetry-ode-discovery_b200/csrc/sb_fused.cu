@@ -669,6 +669,18 @@ int tuning_variant() {
   return v;
 }
 
+int small_variant() {
+  static std::atomic<int> cached{-1};
+  int v = cached.load(std::memory_order_acquire);
+  if (v < 0) {
+    const char* e = getenv("SB_FUSED_VARIANT_SMALL");
+    v = e ? atoi(e) : 0;                       // 0 = per-shape default
+    if (v != 5 && v != 13 && v != 37 && v != 45) v = 0;
+    cached.store(v, std::memory_order_release);
+  }
+  return v;
+}
+
 template <int D, int P, int LEFT, int VAR, int SLOT = 0>
 int launch_fused_var(FusedArgs a, void* ws, int64_t ws_bytes, cudaStream_t s, int slot = 0) {
   using C = Cfg<D, P, VAR>;
@@ -727,7 +739,21 @@ int launch_fused(const FusedArgs& a, void* ws, int64_t ws_bytes, cudaStream_t s,
       default: return launch_fused_var<D, P, LEFT, 15>(a, ws, ws_bytes, s, slot);
     }
   }
-  return launch_fused_var<D, P, LEFT, 5>(a, ws, ws_bytes, s, slot);  // small libraries: empty-barrier ring + folded reduction
+  // small libraries: empty-barrier ring + folded reduction; tile ring / prefetch per shape from the A/B on B200 at
+  // N = 1e8 (median of 15, ms; SB_FUSED_VARIANT_SMALL overrides):   1024x4   2048x3   1024x4+prefetch   2048x3+prefetch
+  //                                                      (2,2) K=6   0.2725   0.2626       0.2758            0.2663
+  //                                                      (2,3) K=10  0.3491   0.3260       0.3237            0.2967
+  //                                                      (3,3) K=20  0.5957   0.5790       0.6455            0.6731
+  // 2048-sample tiles halve the per-tile barrier traffic (4 -> 8 samples per thread and tile); reading the next
+  // sample ahead pays where the loop is short enough to be latency-bound (K = 10) and costs registers / issue slots
+  // where the FMA pipe is the limit (K = 20).
+  const int chosen = small_variant() ? small_variant() : ((D == 2 && P == 3) ? 45 : 13);
+  switch (chosen) {
+    case 13: return launch_fused_var<D, P, LEFT, 13>(a, ws, ws_bytes, s, slot);   // 2048 x 3 ring
+    case 37: return launch_fused_var<D, P, LEFT, 37>(a, ws, ws_bytes, s, slot);   // 1024 x 4 ring + next-sample prefetch
+    case 45: return launch_fused_var<D, P, LEFT, 45>(a, ws, ws_bytes, s, slot);   // 2048 x 3 ring + prefetch
+    default: return launch_fused_var<D, P, LEFT, 5>(a, ws, ws_bytes, s, slot);
+  }
 }
 
 // device (global-alias) address of constant slot `slot` on the current device

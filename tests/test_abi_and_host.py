@@ -276,6 +276,43 @@ def test_launcher_puts_the_hot_path_modules_first():
     assert res.returncode == 0 and res.stdout.split() == ["_sindy_b200_reference_train", "True"], res.stdout + res.stderr
 
 
+@pytest.mark.parametrize("constrained", [False, True])
+def test_batched_seed_sweep_equals_the_serial_sweep(constrained):
+    """All seeds as ONE batched LBFGS problem against the seed-after-seed sweep (torch.optim.LBFGS per
+    seed through train_SIGED_lbfgs(cached_gram=True)): same masks, coefficients to 1e-3 of the largest (the loop's own
+    stopping tolerance). Host logic only: the sufficient statistics come from the oracle instead of the kernel."""
+    import sindy
+    import sweep
+    rng = np.random.default_rng(11)
+    n = 4000
+    x = rng.uniform(-1.5, 1.5, (n, 2)).astype(np.float32)
+    truth = np.array([[0, -0.1, -1, 0, 0, 0], [0, 1, -0.1, 0, 0, 0.0]])
+    dx = (O.theta(x.astype(np.float64), 2) @ truth.T + 0.05 * rng.standard_normal((n, 2))).astype(np.float32)
+    xt, dxt = torch.from_numpy(x), torch.from_numpy(dx)
+    L = [torch.tensor([[0.0, 1.0], [-1.0, 0.0]])] if constrained else []
+
+    def stats_of(xb, dxb):
+        s = O.train_step_sums(xb.numpy(), dxb.numpy(), np.zeros((2, 6)), 2)
+        return {"G": torch.from_numpy(s["gram"]), "b": torch.from_numpy(s["b"]),
+                "yy": torch.tensor((dxb.double() ** 2).sum()), "n": float(xb.shape[0])}
+
+    def make():
+        reg = sindy.SINDyRegression(2, 2, False, False, L_list=L, threshold=0.05, device="cpu", constrain_constant=False)
+        reg.sufficient_statistics = stats_of
+        return reg
+
+    seeds = list(range(6))
+    serial = sweep.run_seed_sweep(xt, dxt, truth, seeds, make, subsample=0.5, lr_sindy=0.1, st_freq=50, threshold=0.05,
+                                  num_epochs=60)
+    batched = sweep.run_seed_sweep_batched(xt, dxt, truth, seeds, make, subsample=0.5, lr_sindy=0.1, st_freq=50,
+                                           threshold=0.05, num_epochs=60)
+    for a, b in zip(serial, batched):
+        assert a["seed"] == b["seed"]
+        assert np.array_equal(a["coefficients"] != 0, b["coefficients"] != 0), (a["coefficients"], b["coefficients"])
+        assert np.abs(a["coefficients"] - b["coefficients"]).max() < 1e-3 * np.abs(a["coefficients"]).max()
+    assert sum(r["correct_form_all"] for r in batched) >= 4
+
+
 def test_lstsq_driver_selection(monkeypatch):
     import sindy
     assert sindy._lstsq_driver({}) == "gels"

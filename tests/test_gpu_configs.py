@@ -122,6 +122,35 @@ def test_live_against_the_reference_on_the_same_gpu(key, tol, tmp_path):
 
 
 @needs_ref
+@pytest.mark.parametrize("key", ["C1", "C2"])
+def test_batched_seed_sweep_is_seed_for_seed_the_entry_point(key, golden, tmp_path):
+    """`sweep_main.py` (all seeds of a cfg as one batched LBFGS problem) replays `main.py:25-77`'s random
+    draws in the reference's order, so seed 0 of the sweep is THE run `python main.py --seed 0 --config <cfg>` makes:
+    same mask as the reference's golden run of that entry point, coefficients within the LBFGS loop's stopping tolerance
+    (1e-3 of the largest); the other seeds of the sweep are independent fits written as seed<k>.npz like main.py does."""
+    import json
+    import subprocess
+    import sys
+    cfg = config_runs.CONFIGS[key]
+    config_runs.prepare_workdir(str(tmp_path), REF, key)
+    out_json = os.path.join(tmp_path, "sweep.json")
+    cmd = [sys.executable, config_runs.LAUNCHER, "--reference", REF, os.path.join(config_runs.PKG, "sweep_main.py"),
+           "--config", cfg["cfg"], "--gpu", "0", "--seeds", "0-5", "--json", out_json]
+    env = dict(os.environ, WANDB_MODE="disabled", SINDY_B200_INIT_RNG="cpu")
+    env.pop("PYTHONPATH", None)
+    res = subprocess.run(cmd, cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=1200)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-3000:]
+    results = json.load(open(out_json))
+    assert [r["seed"] for r in results] == list(range(6))
+    want = golden("configs")[f"{key}_coefficients"]
+    got = np.asarray(results[0]["coefficients"])
+    assert np.array_equal(got != 0, want != 0), f"{got}\n{want}"
+    assert np.abs(got - want).max() <= 1e-3 * np.abs(want).max(), f"{got}\n{want}"
+    assert "Joint success rate" in res.stdout
+    assert os.path.exists(os.path.join(tmp_path, "eval_results", cfg["save_dir"], "seed5.npz"))
+
+
+@needs_ref
 def test_data_generators_through_the_dropin(tmp_path):
     """`python -m data_utils.<ode>` of the reference (README option 2) on this repo's solve_ode_batch: the Python
     right-hand side is identified as a library member and integrated by the CUDA rollout; the files have the reference's
