@@ -275,6 +275,11 @@ int euler_flow_backward(const float* x, const float* v, const float* g_fx, const
 int symreg_r(const float* x, const float* gx, const float* jg, int64_t n, const LibTab& t, const float* w,
              double* out, void* ws, int64_t ws_bytes, cudaStream_t s);
 
+// tensor-core (tcgen05, 3xTF32) WSINDy integrals over many trajectories (sb_wsindy_tc.cu)
+bool wsindy_tc_supported(const LibTab& t, int n_test);
+int wsindy_integrals_tc(const float* x, int64_t n_traj, int64_t T, const LibTab& t, float dt, double t_max, int n_test,
+                        double* G, double* b, cudaStream_t s);
+
 // FP32 peak microbenchmark
 int fp32_peak(int variant, int iters, double* tflops_host, cudaStream_t s);
 

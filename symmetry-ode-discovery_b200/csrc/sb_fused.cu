@@ -860,9 +860,17 @@ template <int D, int P>
 __global__ void __launch_bounds__(256) forward_spec_kernel(const float* __restrict__ x, int64_t n,
                                                            float* __restrict__ y) {
   using C = Cfg<D, P, 1>;
-  for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n; s += (int64_t)gridDim.x * blockDim.x) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // the next sample's x is requested before the current one is expanded: ncu showed the kernel waiting on its own
+  // global loads (long scoreboard 4.97 per issue, round 2) with nothing to overlap them
+  float xn[D];
+  if (s < n) static_for<0, D>([&](auto q) { xn[q] = __ldg(x + s * D + q); });
+  for (; s < n; s += stride) {
     float xs[D], m[C::K];
-    static_for<0, D>([&](auto q) { xs[q] = __ldg(x + s * D + q); });
+    static_for<0, D>([&](auto q) { xs[q] = xn[q]; });
+    const int64_t s2 = s + stride;
+    if (s2 < n) static_for<0, D>([&](auto q) { xn[q] = __ldg(x + s2 * D + q); });
     expand_poly<D, P>(xs, m);
     float2 pred[D][2];
     static_for<0, D>([&](auto i) { pred[i][0] = make_float2(0.f, 0.f); pred[i][1] = make_float2(0.f, 0.f); });

@@ -25,6 +25,8 @@
 //     (fp32 accumulation runs over at most 2048 samples), no cross-thread reduction, no atomics, deterministic.
 // Algorithmic cost per time sample: (K−1−d) + 2·n_test·(K+d) flop (test functions amortised over the batch) against
 // 4·d bytes => FP32-bound by two orders of magnitude (d=2,K=10: 1207 flop / 8 B; d=3,K=56: 5952 flop / 12 B).
+#include <cstdlib>
+
 #include "sb_common.cuh"
 #include "sb_tma.cuh"
 
@@ -356,6 +358,12 @@ int wsindy_integrals(const float* x, int64_t n_traj, int64_t T, const LibTab& t,
   a.x = x; a.T = T; a.dt_f = dt; a.tmax_f = (float)t_max; a.c1_f = (float)sqrt(2.0 / t_max);
   a.n_test = n_test; a.G = G; a.b = b;
   const bool poly = !t.sine && !t.exp_;
+  // SB_WSINDY_TC=1: tensor-core kernel (sb_wsindy_tc.cu) for batches; default off until it is the measured winner
+  {
+    const char* e = getenv("SB_WSINDY_TC");
+    if (e && e[0] == '1' && T > 0 && n_traj >= kBatchedMinTraj && wsindy_tc_supported(t, n_test))
+      return wsindy_integrals_tc(x, n_traj, T, t, dt, t_max, n_test, G, b, s);
+  }
   if (poly && T > 0 && n_test <= 64 && n_traj >= kBatchedMinTraj && n_traj <= (int64_t)0x7fffffff * 4) {
 #define X(D, P) if (t.d == D && t.n_poly == n_poly_terms(D, P)) return launch_batched<D, P>(a, n_traj, s);
     X(2, 2) X(2, 3) X(3, 2) X(3, 3) X(3, 5)
