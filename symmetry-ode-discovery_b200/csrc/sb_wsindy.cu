@@ -358,10 +358,11 @@ int wsindy_integrals(const float* x, int64_t n_traj, int64_t T, const LibTab& t,
   a.x = x; a.T = T; a.dt_f = dt; a.tmax_f = (float)t_max; a.c1_f = (float)sqrt(2.0 / t_max);
   a.n_test = n_test; a.G = G; a.b = b;
   const bool poly = !t.sine && !t.exp_;
-  // SB_WSINDY_TC=1: tensor-core kernel (sb_wsindy_tc.cu) for batches; default off until it is the measured winner
+  // batches take the tensor-core kernel (sb_wsindy_tc.cu: 1.25-2.2x the CUDA-core batched kernel below, measured);
+  // SB_WSINDY_TC=0 selects the CUDA-core kernel (A/B, and the more accurate of the two: 1e-6 against 1.5e-5 on G)
   {
     const char* e = getenv("SB_WSINDY_TC");
-    if (e && e[0] == '1' && T > 0 && n_traj >= kBatchedMinTraj && wsindy_tc_supported(t, n_test))
+    if (!(e && e[0] == '0') && T > 0 && n_traj >= kBatchedMinTraj && wsindy_tc_supported(t, n_test))
       return wsindy_integrals_tc(x, n_traj, T, t, dt, t_max, n_test, G, b, s);
   }
   if (poly && T > 0 && n_test <= 64 && n_traj >= kBatchedMinTraj && n_traj <= (int64_t)0x7fffffff * 4) {

@@ -387,12 +387,14 @@ def test_golden_wsindy(nat, golden):
 
 @pytest.mark.parametrize("d,p,n_traj,T,n_test", [(2, 3, 37, 1000, 50), (2, 2, 16, 333, 50), (3, 2, 9, 70, 7),
                                                   (3, 3, 24, 2049, 64), (3, 5, 13, 1500, 50)])
-def test_wsindy_batched_kernel(nat, d, p, n_traj, T, n_test):
-    """WSINDy over many trajectories (SURVEY §8a a10 "at scale", §8e): the batched kernel (one CTA = a group of
-    trajectories, test functions generated once per time tile and shared, register-tiled contraction) against the CPU
-    oracle of `sindy.py:337-362` per trajectory and against the per-test-function kernel (taken below 8 trajectories).
-    Ragged sizes: trajectory counts that do not fill the last CTA, T that is not a multiple of the 64-sample tile nor
-    of the 1024-sample flush period, fewer than 64 test functions."""
+@pytest.mark.parametrize("tc", ["1", "0"])
+def test_wsindy_batched_kernel(nat, d, p, n_traj, T, n_test, tc, monkeypatch):
+    """WSINDy over many trajectories (SURVEY §8a a10 "at scale", §8e): the tensor-core kernel (tc = 1: tcgen05 3xTF32,
+    operands generated into the UMMA layout, accumulators in TMEM) and the CUDA-core batched kernel (tc = 0: register-
+    tiled SIMT contraction) against the CPU oracle of `sindy.py:337-362` per trajectory and against the per-test-function
+    kernel (taken below 8 trajectories). Ragged sizes: trajectory counts that do not fill the last CTA, T that is not a
+    multiple of the time tile nor of the accumulator drain period, fewer than 64 test functions."""
+    monkeypatch.setenv("SB_WSINDY_TC", tc)
     lib = nat.Library(d, p)
     rng = np.random.default_rng(100 * d + p)
     dt = 0.002

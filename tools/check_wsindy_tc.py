@@ -18,7 +18,7 @@ for (d, p, ntr, T, nt) in ((2, 3, 37, 1000, 50), (3, 5, 13, 1500, 50), (2, 2, 16
         Go, bo = O.wsindy_integrals(x[r], 0.002, T * 0.002, p, n_test=nt)
         errs.append((np.abs(G[r].cpu().numpy() - Go).max() / np.abs(Go).max(), np.abs(b[r].cpu().numpy() - bo).max() / np.abs(bo).max()))
     print("tc=" + mode, (d, p, ntr, T, nt), "max rel err G/b:", max(e[0] for e in errs), max(e[1] for e in errs), flush=True)
-for (d, p, ntr) in ((2, 3, 18944), (3, 5, 4736), (2, 2, 18944), (3, 3, 9472)):
+for (d, p, ntr) in ((2, 3, 18944), (2, 3, 56832), (3, 5, 4736), (2, 2, 18944), (3, 3, 9472)):
     lib = native.Library(d, p)
     x = torch.rand(ntr, 8000, d, device="cuda") * 0.8 + 0.2
     native.wsindy_integrals(x, lib, 0.002, 16.0, 50); torch.cuda.synchronize()
