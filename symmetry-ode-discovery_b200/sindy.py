@@ -154,8 +154,12 @@ class SINDyRegression(nn.Module):
         self.Xi = self._current_Xi()
         W = self.Xi * self.mask
         poly = not (self.include_sine or self.include_exp)
+        needs_z_grad = torch.is_grad_enabled() and torch.is_tensor(z) and z.requires_grad
         if method == 'auto':
-            method = 'gram' if poly else 'jvp'
+            method = 'gram' if (poly and not needs_z_grad) else 'jvp'
+        if method == 'gram' and needs_z_grad:
+            raise ValueError("lie_reg_loss(method='gram') differentiates with respect to the parameters only (the Gram "
+                             "matrix of z is formed without a graph); use method='jvp' when z carries a gradient")
         if method == 'gram':
             key = tuple(float(q) for v in generators for q in torch.as_tensor(v).flatten().tolist())
             if getattr(self, '_lie_key', None) != key:
