@@ -755,6 +755,47 @@ def extras(native, dev, peaks, fp32_peak):
     out["stlsq_solve_SINDy_C5"] = {"samples_per_s": n / (ms * 1e-3), "ms": ms, "recovered_support_is_truth": support_ok,
                                    "max_coef_err_rel": coef_err}
     del x, dx, dxn
+    # fused symmetry-regulariser kernels on config 3's library (2, 2, exp), 1e7 samples: the Euler flow map with its JVP
+    # (forward + reverse sweep, one launch each) beside the operator-by-operator composition the reference's call
+    # pattern produces (10 Python Euler steps under a double vjp), and the streaming reversed regulariser
+    try:
+        from torch.autograd.functional import jvp as _jvp
+        from sindy_b200 import ops as _ops
+        l8 = native.Library(2, 2, False, True)
+        n7 = 10 ** 7
+        xs = torch.log(torch.rand(n7, 2, device=dev, generator=gen) * 0.8 + 0.1)
+        vs = torch.randn(n7, 2, device=dev, generator=gen)
+        gs = torch.randn(n7, 2, device=dev, generator=gen)
+        W8 = (0.3 * torch.randn(2, l8.K, device=dev, generator=gen)).requires_grad_(True)
+
+        def fused_fb():
+            vv = vs.clone().requires_grad_(True)
+            fx, jv = _ops.euler_flow(xs, vv, W8, l8, 0.01, 10)
+            torch.autograd.grad((fx * gs).sum() + (jv * gs).sum(), (W8, vv))
+
+        def composed_fb():
+            vv = vs.clone().requires_grad_(True)
+
+            def flow(q):
+                for _ in range(10):
+                    q = q + 0.01 * _ops.sindy_forward(q, W8, l8)
+                return q
+            fx, jv = _jvp(flow, xs, vv, create_graph=True)
+            torch.autograd.grad((fx * gs).sum() + (jv * gs).sum(), (W8, vv))
+
+        ms_fused = timed(fused_fb, reps=3)
+        ms_comp = timed(composed_fb, reps=3)
+        gxs = xs + 0.05 * vs
+        Jg = (torch.eye(2, device=dev).expand(n7, 2, 2) + 0.1 * torch.randn(n7, 2, 2, device=dev, generator=gen)).contiguous()
+        ms_r = timed(lambda: native.symreg_r(xs, gxs, Jg, W8.detach(), l8), reps=3)
+        out["symreg_kernels_config3_library_1e7"] = {
+            "euler_flow_jvp_fwd_bwd_fused_ms": ms_fused, "same_composed_through_autograd_ms": ms_comp,
+            "speedup": ms_comp / ms_fused, "flow_samples_per_s": n7 / (ms_fused * 1e-3),
+            "symreg_r_streaming_ms": ms_r, "symreg_r_samples_per_s": n7 / (ms_r * 1e-3),
+            "symreg_r_hbm_gbs": 4 * (2 + 2 + 4) * n7 / (ms_r * 1e-3) / 1e9}
+        del xs, vs, gs, gxs, Jg
+    except Exception as exc:   # noqa: BLE001
+        out["symreg_kernels_config3_library_1e7"] = {"error": repr(exc)}
     # WSINDy weak-form integrals over MANY trajectories: batches of Sel'kov-shaped trajectories
     # (T = 8000, 50 test functions) for the config-4 library and for the C5 library; algorithmic cost per time sample
     # (K−1−d) + 2·n_test·(K+d) flop (test functions are generated once per time tile for the whole batch) and 4·d bytes

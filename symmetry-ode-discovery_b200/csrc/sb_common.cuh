@@ -125,6 +125,36 @@ __device__ __forceinline__ void expand_poly(const T (&x)[D], T (&m)[Poly<D, P>::
   });
 }
 
+// Library CODE of the specialised kernels: PC = poly_order + 10·include_exp + 20·include_sine, so that the polynomial
+// shapes keep their plain degree (PC = P) and config 3's library (degree 2 + exp) is PC = 12.
+template <int D, int PC>
+struct LibCode {
+  static constexpr int P = PC % 10;
+  static constexpr int E = (PC / 10) % 2;
+  static constexpr int S = PC / 20;
+  static constexpr int NP = Poly<D, P>::K;
+  static constexpr int K = NP + D * (S + E);
+};
+template <int D, int PC>
+__host__ __device__ inline bool lib_matches(const LibTab& t) {
+  using L = LibCode<D, PC>;
+  return t.d == D && t.n_poly == L::NP && (t.sine != 0) == (L::S != 0) && (t.exp_ != 0) == (L::E != 0);
+}
+// Θ(x) for a library code: the polynomial block, then sin(x_j), then exp(x_j) (`sindy.py:7-30`)
+template <int D, int PC>
+__device__ __forceinline__ void expand_lib(const float (&x)[D], float (&m)[LibCode<D, PC>::K]) {
+  using L = LibCode<D, PC>;
+  if constexpr (L::S == 0 && L::E == 0) {
+    expand_poly<D, L::P>(x, m);
+  } else {
+    float mp[L::NP];
+    expand_poly<D, L::P>(x, mp);
+    static_for<0, L::NP>([&](auto k) { m[k] = mp[k]; });
+    if constexpr (L::S) static_for<0, D>([&](auto j) { m[L::NP + j] = sinf(x[j]); });
+    if constexpr (L::E) static_for<0, D>([&](auto j) { m[L::NP + D * L::S + j] = expf(x[j]); });
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // reductions
 // ---------------------------------------------------------------------------------------------

@@ -70,7 +70,7 @@ __device__ __forceinline__ void stamp(unsigned long long* trace, int slot) {
 //          accumulation of equation i can fill the dependent prediction chains of equation i+1
 template <int D, int P, int VAR = 1>
 struct Cfg {
-  static constexpr int K = Poly<D, P>::K;
+  static constexpr int K = LibCode<D, P>::K;   // P is a library CODE (sb_common.cuh): degree, +10 exp, +20 sine
   static constexpr int K2 = (K + 1) / 2;     // packed column pairs
   static constexpr int NV = D * K + 1;       // values reduced per CTA (grad + loss)
   static constexpr int kRow = (NV + 3) & ~3; // floats per partial row in the workspace (rows stay 16-byte aligned)
@@ -86,8 +86,11 @@ struct Cfg {
   static constexpr bool kFoldReduce = (VAR & 4) != 0;
   static constexpr bool kEqOrder = (VAR & 128) != 0;
   // accumulators dominate the register budget: D*K2*2 of them
-  static constexpr int kMinBlocks = (D * K2 * 2 + K > 150) ? 1 : ((D * K2 * 2 + K > 40) ? 2 : 3);
   static constexpr size_t kSmemData = (size_t)kStages * 2 * kTile * D * sizeof(float);
+  // resident CTAs per SM the register budget is sized for: the accumulators (D*K2*2) dominate; a ring that fills more
+  // than half of the shared memory leaves room for one CTA only, which may then use the whole register file
+  static constexpr int kMinBlocks = (D * K2 * 2 + K > 150 || kSmemData > 110 * 1024) ? 1
+                                    : ((D * K2 * 2 + K > 40 || kSmemData > 72 * 1024) ? 2 : 3);
   static constexpr size_t kSmemBytes = kSmemData + (2 * kStages + 1) * sizeof(uint64_t) + 16;
 };
 
@@ -100,7 +103,7 @@ __device__ __forceinline__ void accumulate_sample(const float (&xs)[D], const fl
   using C = Cfg<D, P, VAR>;
   constexpr int w_off = SLOT * kWSlotPairs;
   float m[C::K];
-  expand_poly<D, P>(xs, m);
+  expand_lib<D, P>(xs, m);
   float2 m2[C::K2];
   static_for<0, C::K2>([&](auto kc) {
     constexpr int kk = kc;
@@ -663,7 +666,7 @@ int tuning_variant() {
     // only x of the next sample ahead (3 registers; its LDS shows as the loop's largest short-scoreboard stall) made no
     // difference either: 1.3325 against 1.3300.
     v = e ? atoi(e) : 15;
-    if (v < 0 || v > 511) v = 15;
+    if (v < 0 || v > 1023) v = 15;
     cached.store(v, std::memory_order_release);
   }
   return v;
@@ -746,7 +749,9 @@ int launch_fused(const FusedArgs& a, void* ws, int64_t ws_bytes, cudaStream_t s,
   //                                                      (3,3) K=20  0.5957   0.5790       0.6455            0.6731
   // 2048-sample tiles halve the per-tile barrier traffic (4 -> 8 samples per thread and tile); reading the next
   // sample ahead pays where the loop is short enough to be latency-bound (K = 10) and costs registers / issue slots
-  // where the FMA pipe is the limit (K = 20).
+  // where the FMA pipe is the limit (K = 20). Two samples per thread and iteration (two independent chains) was also
+  // tried on the 2048x3 ring: (2,3) 0.327, (3,3) 0.686 — slower (170 registers, the second expansion competes for the
+  // same FMA pipe); removed.
   const int chosen = small_variant() ? small_variant() : ((D == 2 && P == 3) ? 45 : 13);
   switch (chosen) {
     case 13: return launch_fused_var<D, P, LEFT, 13>(a, ws, ws_bytes, s, slot);   // 2048 x 3 ring
@@ -871,7 +876,7 @@ __global__ void __launch_bounds__(256) forward_spec_kernel(const float* __restri
     static_for<0, D>([&](auto q) { xs[q] = xn[q]; });
     const int64_t s2 = s + stride;
     if (s2 < n) static_for<0, D>([&](auto q) { xn[q] = __ldg(x + s2 * D + q); });
-    expand_poly<D, P>(xs, m);
+    expand_lib<D, P>(xs, m);
     float2 pred[D][2];
     static_for<0, D>([&](auto i) { pred[i][0] = make_float2(0.f, 0.f); pred[i][1] = make_float2(0.f, 0.f); });
     static_for<0, C::K2>([&](auto kc) {
@@ -911,18 +916,18 @@ int run_weighted_sums(const float* x, const float* g, int64_t n, double* out, vo
 }
 
 // the list of specialised libraries (polynomial only)
-#define SB_FUSED_SHAPES(X) X(2, 2) X(2, 3) X(3, 2) X(3, 3) X(3, 5)
+// (d, library code): the polynomial libraries and config 3's (2, degree 2 + exp) = code 12
+#define SB_FUSED_SHAPES(X) X(2, 2) X(2, 3) X(3, 2) X(3, 3) X(3, 5) X(2, 12)
 
 }  // namespace
 
 void fused_set_trace(unsigned long long* p) { g_trace = p; }
 
 bool fused_supported(const LibTab& t, uint32_t flags) {
-  if (t.sine || t.exp_) return false;
   if (flags & SB_STEP_GRAM) return false;
   // LOSS without GRAD runs the generic residual rows (the fused kernel always accumulates the gradient)
   if ((flags & SB_STEP_LOSS) && !(flags & SB_STEP_GRAD)) return false;
-#define X(D, P) if (t.d == D && t.n_poly == n_poly_terms(D, P)) return true;
+#define X(D, P) if (lib_matches<D, P>(t)) return true;
   SB_FUSED_SHAPES(X)
 #undef X
   return false;
@@ -930,14 +935,14 @@ bool fused_supported(const LibTab& t, uint32_t flags) {
 
 const char* fused_variant_name(const LibTab& t, uint32_t flags) {
   (void)flags;
-#define X(D, P) if (t.d == D && t.n_poly == n_poly_terms(D, P)) return "fused_tma<" #D "," #P ">";
+#define X(D, P) if (lib_matches<D, P>(t)) return "fused_tma<" #D "," #P ">";
   SB_FUSED_SHAPES(X)
 #undef X
   return "generic";
 }
 
 int fused_forward(const float* x, int64_t n, const LibTab& t, const float* w, float* y, cudaStream_t s) {
-#define X(D, P) if (t.d == D && t.n_poly == n_poly_terms(D, P)) return run_forward<D, P>(x, n, w, y, s);
+#define X(D, P) if (lib_matches<D, P>(t)) return run_forward<D, P>(x, n, w, y, s);
   SB_FUSED_SHAPES(X)
 #undef X
   set_error("no specialised forward for d=%d K=%d", t.d, t.K);
@@ -947,7 +952,7 @@ int fused_forward(const float* x, int64_t n, const LibTab& t, const float* w, fl
 int fused_weighted_sums(const float* x, const float* g, int64_t n, const LibTab& t, double* out, void* ws,
                         int64_t ws_bytes, cudaStream_t s) {
 #define X(D, P) \
-  if (t.d == D && t.n_poly == n_poly_terms(D, P)) return run_weighted_sums<D, P>(x, g, n, out, ws, ws_bytes, s);
+  if (lib_matches<D, P>(t)) return run_weighted_sums<D, P>(x, g, n, out, ws, ws_bytes, s);
   SB_FUSED_SHAPES(X)
 #undef X
   set_error("no fused kernel for d=%d K=%d", t.d, t.K);
@@ -959,7 +964,7 @@ int64_t fused_workspace_bytes(const LibTab& t) {
 }
 
 int fused_load_w(const LibTab& t, const float* xi, const float* mask, cudaStream_t s) {
-#define X(D, P) if (t.d == D && t.n_poly == n_poly_terms(D, P)) return upload_w<D, P>(xi, mask, 1, s);
+#define X(D, P) if (lib_matches<D, P>(t)) return upload_w<D, P>(xi, mask, 1, s);
   SB_FUSED_SHAPES(X)
 #undef X
   set_error("no fused kernel for d=%d K=%d", t.d, t.K);
@@ -970,7 +975,7 @@ int fused_train_step(const float* x, const float* dx, int64_t n, const LibTab& t
                      uint32_t flags, double* out, const ClosureOut* co, const PeerArgs* peer, void* ws,
                      int64_t ws_bytes, cudaStream_t s, const FitArgs* fit) {
 #define X(D, P)                                                  \
-  if (t.d == D && t.n_poly == n_poly_terms(D, P))                \
+  if (lib_matches<D, P>(t))                \
     return run_fused<D, P>(x, dx, n, w, mask, flags, out, co, peer, ws, ws_bytes, s, fit);
   SB_FUSED_SHAPES(X)
 #undef X

@@ -162,7 +162,7 @@ __device__ __forceinline__ void wb_contract(const float* __restrict__ th, const 
     });
     const float4 va = vs[(t * 2 + 0) * 8], vb = vs[(t * 2 + 1) * 8];
     const float v[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
-    float dv[8];
+    float dv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if constexpr (kLast) {
       const float4 da = vd[(t * 2 + 0) * 8], db = vd[(t * 2 + 1) * 8];
       dv[0] = da.x; dv[1] = da.y; dv[2] = da.z; dv[3] = da.w; dv[4] = db.x; dv[5] = db.y; dv[6] = db.z; dv[7] = db.w;

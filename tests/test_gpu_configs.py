@@ -171,6 +171,39 @@ def test_data_generators_through_the_dropin(tmp_path):
         assert np.abs(th @ truth.T - dx.double().numpy().reshape(-1, 2)).max() < 1e-5
 
 
+def test_gp_smoother_at_full_length_reproduces_the_references_data_set():
+    """The GP smoother (`data_utils/smoothing.py:155-196`) at the reference's REAL size — T = 10^4 samples, 50
+    trajectories (the C1 data set; ≈ 5 min of dense float64 LAPACK per file in the reference) — against the data set the
+    reference's own generator produced (tests/golden/data/dosc-train-noise20-gp-*.pt, oracle/gen_config_data.py, seed
+    1001). The test replays that generator on this repo's modules: the same NumPy draws (initial conditions, then the
+    noise), the float64 RK4 rollout on the GPU (1e-11 of the reference's), the device Cholesky smoother; then the
+    reference's subsampling. Stored fixture is float32: X to 2e-6, dX to 5e-4 of the largest entry."""
+    import time
+    from data_utils import ode, smoothing, systems
+    np.random.seed(1001)
+    ics = []
+    for _ in range(50):                                   # `damped_oscillator.py:10-17`
+        r = np.random.uniform(0.5, 2)
+        th = np.random.uniform(0, 2 * np.pi)
+        ics.append(np.array([r * np.cos(th), r * np.sin(th)]))
+    x0 = np.array(ics)
+    x, dx = ode.solve_ode_batch(systems.dosc(), x0, dt=0.002, num_steps=10000)
+    x_std = np.std(x, axis=(0, 1))                        # `data_utils/ode.py:33-37`
+    x += np.random.randn(*x.shape) * 0.2 * x_std
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    dX, X = smoothing.num_diff_gp(x, 0.002, noise_level=0.2, std_base=x_std, sigma_in=0.1)
+    took = time.perf_counter() - t0
+    X = np.transpose(X[::100], (1, 0, 2))
+    dX = np.transpose(dX[::100], (1, 0, 2))
+    want_x = torch.load(os.path.join(config_runs.DATA, "dosc-train-noise20-gp-x.pt")).numpy()
+    want_dx = torch.load(os.path.join(config_runs.DATA, "dosc-train-noise20-gp-dx.pt")).numpy()
+    ex = np.abs(X - want_x).max() / np.abs(want_x).max()
+    edx = np.abs(dX - want_dx).max() / np.abs(want_dx).max()
+    print(f"GP smoother T=1e4 x 50 trajectories: {took:.2f} s on the GPU; X err {ex:.2e}, dX err {edx:.2e}")
+    assert ex < 2e-6 and edx < 5e-4, (ex, edx)
+
+
 def config_runs_truth(name):
     """`evaluation/eval_eq.py:88-105` restated (test infrastructure)."""
     return {"lv": np.array([[2 / 3, 0, 0, 0, 0, 0, 0, -4 / 3], [-1.0, 0, 0, 0, 0, 0, 1.0, 0]]),
