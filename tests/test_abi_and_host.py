@@ -385,7 +385,7 @@ def test_fit_step_argument_validation_without_a_device():
     bad = native._CFitOptions(7, 1e-3, 0.9, 0.999, 1e-8, 1.0, 0.0, 0.0, None)
     assert call(o=ctypes.byref(bad)) == -1 and b"optimiser" in lib.sb_last_error()
     assert call(x=ctypes.c_void_p(20)) == -2 and b"aligned" in lib.sb_last_error()       # misaligned input
-    Lg = native._CLibrary(2, 2, 0, 1)                                                    # exp column: no fused kernel
+    Lg = native._CLibrary(2, 2, 1, 0)                                                    # sine columns: no fused kernel
     assert lib.sb_load_w(ctypes.byref(Lg), one, None, None) == -2
     assert lib.sb_load_w(ctypes.byref(L), None, None, None) == -1
 
