@@ -265,6 +265,35 @@ int sb_rollout(const void* x0, int64_t n_ics, const sb_library* lib, const void*
 int sb_wsindy_integrals(const float* x, int64_t n_traj, int64_t T, const sb_library* lib, float dt,
                         double t_max, int n_test, double* G, double* b, void* stream);
 
+/* Frozen-MLP chains on the tensor cores: the encoder / decoder of the frozen autoencoder
+ * (`autoencoder.py:38-66`: Linear [+ BatchNorm in eval mode, folded into the weights by the host] + ReLU, hidden width a
+ * multiple of 256, thin first / last layers of width ≤ 8) as evaluated inside `symmreg_i` / `symmreg_f` /
+ * `precompute_symmreg_r` (`model_utils.py:8-211`): values, Jacobian-vector products (`jvp(autoencoder.decoder, z, v)`,
+ * `autoencoder.py:110-113, 132`) and the transpose products `loss.backward()` needs. Every wide layer is
+ *   C = epilogue(A · Bᵀ),  A (m × k), B (n × k) frozen,  epilogue ∈ {0: + bias, 1: ReLU(· + bias), 2: ReLU mask of
+ *   another activation tensor R (C = R > 0 ? · : 0)}  — tangents use B = W, R = this layer's value output; cotangents
+ *   use B = Wᵀ, R = the layer's value input —
+ * computed by one persistent tcgen05 kernel in 3×TF32 (fp32-faithful). Activations are kept in HBM in the PANEL FORMAT
+ * the tensor core consumes: sb_mlp_panel_bytes(m, f) bytes for an (m × f) tensor (rows padded to 128; per 128-row tile and
+ * 16-feature block a contiguous 16 KB [tf32-hi | lo] pair in the canonical K-major core-matrix layout), so that a
+ * layer's epilogue writes the next layer's operand and the operand ring is filled by plain bulk copies.
+ *  - sb_mlp_pack_weights: B[n][k] = w[n·k_dim + k] (transpose = 0) or w[k·n + n_idx] (transpose = 1) → packed, 8·n·k bytes.
+ *  - sb_mlp_pack_rows / sb_mlp_unpack_rows: (m × f) row-major fp32 ↔ panel format (tests, wide inputs).
+ *  - sb_mlp_thin_in: C = epilogue(x · wᵀ [+ bias]), x (m × in_dim ≤ 8) row-major, w (f × in_dim), panel-format output.
+ *  - sb_mlp_thin_out: y (m × out_dim ≤ 8, row-major) = A · wᵀ [+ bias], A in panel format, w (out_dim × f).
+ *  - sb_mlp_gemm: the wide layer above; bias (n floats) and mask_panel may be NULL as the mode allows.
+ * All pointers to panel / packed buffers must be 16-byte aligned. */
+int64_t sb_mlp_panel_bytes(int64_t m, int f);
+int sb_mlp_pack_weights(const float* w, int n, int k, int transpose, void* packed, void* stream);
+int sb_mlp_pack_rows(const float* x, int64_t m, int f, void* panel, void* stream);
+int sb_mlp_unpack_rows(const void* panel, int64_t m, int f, float* x, void* stream);
+int sb_mlp_thin_in(const float* x, int64_t m, int in_dim, const float* w, const float* bias, const void* mask_panel,
+                   int f, int mode, void* c_panel, void* stream);
+int sb_mlp_thin_out(const void* a_panel, int64_t m, int f, const float* w, const float* bias, int out_dim, float* y,
+                    void* stream);
+int sb_mlp_gemm(const void* a_panel, int64_t m, int k, const void* w_packed, int n, const float* bias,
+                const void* mask_panel, int mode, void* c_panel, void* stream);
+
 /* Debug/profiling aid: while dev_buf (device memory, 16 uint64 per CTA, at least 16·592 words) is set, every fused
  * kernel launched afterwards records %globaltimer stamps of its phases per CTA: 0 entry, 1 first tile landed, 2 end of
  * the sample loop, 3 partial written + ticket taken, and for the last block 4 totals ready, 5 after the peer exchange,

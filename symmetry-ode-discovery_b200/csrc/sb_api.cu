@@ -438,6 +438,59 @@ int sb_symreg_r(const float* x, const float* gx, const float* jgx, int64_t n, co
   return symreg_r(x, gx, jgx, n, t, w, out, ws, ws_bytes, (cudaStream_t)stream);
 }
 
+static int check_16(const void* p, const char* name) {
+  if (!p) { set_error("%s is NULL", name); return SB_ERR_INVALID; }
+  if (reinterpret_cast<uintptr_t>(p) & 15u) { set_error("%s must be 16-byte aligned", name); return SB_ERR_INVALID; }
+  return SB_OK;
+}
+
+int64_t sb_mlp_panel_bytes(int64_t m, int f) { return (m < 0 || f <= 0) ? 0 : mlp_panel_bytes(m, f); }
+
+int sb_mlp_pack_weights(const float* w, int n, int k, int transpose, void* packed, void* stream) {
+  SB_TRY(check_ptr(w, "w")); SB_TRY(check_16(packed, "packed"));
+  return mlp_pack_weights(w, n, k, transpose, packed, (cudaStream_t)stream);
+}
+
+int sb_mlp_pack_rows(const float* x, int64_t m, int f, void* panel, void* stream) {
+  if (m < 0) { set_error("bad size m=%lld", (long long)m); return SB_ERR_INVALID; }
+  SB_TRY(check_16(panel, "panel"));
+  if (m > 0) SB_TRY(check_16(x, "x"));
+  return mlp_pack_rows(x, m, f, panel, (cudaStream_t)stream);
+}
+
+int sb_mlp_unpack_rows(const void* panel, int64_t m, int f, float* x, void* stream) {
+  if (m < 0) { set_error("bad size m=%lld", (long long)m); return SB_ERR_INVALID; }
+  SB_TRY(check_16(panel, "panel"));
+  if (m > 0) SB_TRY(check_16(x, "x"));
+  return mlp_unpack_rows(panel, m, f, x, (cudaStream_t)stream);
+}
+
+int sb_mlp_gemm(const void* a_panel, int64_t m, int k, const void* w_packed, int n, const float* bias,
+                const void* mask_panel, int mode, void* c_panel, void* stream) {
+  if (m < 0) { set_error("bad size m=%lld", (long long)m); return SB_ERR_INVALID; }
+  SB_TRY(check_16(a_panel, "a_panel")); SB_TRY(check_16(w_packed, "w_packed")); SB_TRY(check_16(c_panel, "c_panel"));
+  if (bias) SB_TRY(check_16(bias, "bias"));
+  if (mask_panel) SB_TRY(check_16(mask_panel, "mask_panel"));
+  return mlp_gemm(a_panel, m, k, w_packed, n, bias, mask_panel, mode, c_panel, (cudaStream_t)stream);
+}
+
+int sb_mlp_thin_in(const float* x, int64_t m, int in_dim, const float* w, const float* bias, const void* mask_panel,
+                   int f, int mode, void* c_panel, void* stream) {
+  if (m < 0) { set_error("bad size m=%lld", (long long)m); return SB_ERR_INVALID; }
+  SB_TRY(check_ptr(w, "w")); SB_TRY(check_16(c_panel, "c_panel"));
+  if (m > 0) SB_TRY(check_ptr(x, "x"));
+  if (mask_panel) SB_TRY(check_16(mask_panel, "mask_panel"));
+  return mlp_thin_in(x, m, in_dim, w, bias, mask_panel, f, mode, c_panel, (cudaStream_t)stream);
+}
+
+int sb_mlp_thin_out(const void* a_panel, int64_t m, int f, const float* w, const float* bias, int out_dim, float* y,
+                    void* stream) {
+  if (m < 0) { set_error("bad size m=%lld", (long long)m); return SB_ERR_INVALID; }
+  SB_TRY(check_16(a_panel, "a_panel")); SB_TRY(check_ptr(w, "w"));
+  if (m > 0) SB_TRY(check_ptr(y, "y"));
+  return mlp_thin_out(a_panel, m, f, w, bias, out_dim, y, (cudaStream_t)stream);
+}
+
 void sb_debug_trace(void* dev_buf) { fused_set_trace(reinterpret_cast<unsigned long long*>(dev_buf)); }
 
 int sb_fp32_peak(int variant, int iters, double* tflops_host, void* stream) {

@@ -310,6 +310,18 @@ bool wsindy_tc_supported(const LibTab& t, int n_test);
 int wsindy_integrals_tc(const float* x, int64_t n_traj, int64_t T, const LibTab& t, float dt, double t_max, int n_test,
                         double* G, double* b, cudaStream_t s);
 
+// frozen-MLP chains on the tensor cores (sb_mlp.cu): panel-format activations, 3xTF32 tcgen05 GEMM with fused epilogue
+int64_t mlp_panel_bytes(int64_t m, int f);
+int mlp_pack_weights(const float* w, int n, int k, int transpose, void* packed, cudaStream_t s);
+int mlp_pack_rows(const float* x, int64_t m, int f, void* packed, cudaStream_t s);
+int mlp_unpack_rows(const void* packed, int64_t m, int f, float* x, cudaStream_t s);
+int mlp_gemm(const void* a_panel, int64_t m, int k, const void* w_packed, int n, const float* bias,
+             const void* mask_panel, int mode, void* c_panel, cudaStream_t s);
+int mlp_thin_in(const float* x, int64_t m, int in_dim, const float* w, const float* bias, const void* mask_panel,
+                int f, int mode, void* c_panel, cudaStream_t s);
+int mlp_thin_out(const void* a_panel, int64_t m, int f, const float* w, const float* bias, int out_dim, float* y,
+                 cudaStream_t s);
+
 // FP32 peak microbenchmark
 int fp32_peak(int variant, int iters, double* tflops_host, cudaStream_t s);
 

@@ -15,6 +15,9 @@ from functools import partial
 import torch
 from torch.autograd.functional import jvp
 
+import os
+
+from sindy_b200 import mlp as _mlp
 from sindy_b200 import native, ops
 
 __all__ = [
@@ -60,14 +63,43 @@ class EulerFlowMap:
         return odeint(self.regressor, x, self.t, self.dt)
 
     def jvp(self, x, v, require_grad=True):
-        if self._fused(x) and not (torch.is_grad_enabled() and x.requires_grad):
+        # first-order differentiable in x, v and Ξ (sb_euler_flow_backward carries the second derivatives of the library
+        # that dL/dx needs). `symmreg_i` hands in x = x_fx[:, 0], a view of a tensor that requires grad because its OTHER
+        # half is f(x): the fused launch must not be lost to that flag.
+        if self._fused(x):
             return ops.euler_flow(x, v, self._w(), self.regressor.library, self.dt, self.n_steps)
         return _jvp_fn(require_grad)(lambda q: odeint(self.regressor, q, self.t, self.dt), x, v)
 
 
+def _fast_ae(autoencoder, x):
+    """(encoder, decoder) on the tensor cores (`sindy_b200.mlp.FrozenMLP`) when the autoencoder is the reference's MLP,
+    frozen, in eval mode and x lives on the GPU; None keeps the PyTorch modules. SINDY_B200_AE_MLP=0 switches it off."""
+    if not (torch.is_tensor(x) and x.is_cuda) or os.environ.get("SINDY_B200_AE_MLP", "1") == "0":
+        return None
+    return _mlp.accelerate(autoencoder)
+
+
+def _encode(autoencoder, x):
+    fast = _fast_ae(autoencoder, x)
+    return fast[0].value(x) if fast is not None else autoencoder.encode(x)
+
+
+def _decode(autoencoder, z):
+    fast = _fast_ae(autoencoder, z)
+    return fast[1].value(z) if fast is not None else autoencoder.decode(z)
+
+
+def _decoder_tangent(autoencoder, z, v, require_grad):
+    """J_decoder(z)·v (`jvp(autoencoder.decoder, z, v)[1]`, `model_utils.py:32`)."""
+    fast = _fast_ae(autoencoder, z)
+    if fast is not None:
+        return fast[1].value_and_jvp(z, v)[1]
+    return _jvp_fn(require_grad)(autoencoder.decoder, z, v=v)[1]
+
+
 def _centred_latent(autoencoder, x, normalize, z_mean):
     """z = encode(x) − centre, centre = batch mean ('in_batch') or z_mean / last BatchNorm bias ('global')."""
-    z = autoencoder.encode(x)
+    z = _encode(autoencoder, x)
     if normalize == 'in_batch':
         z = z - z.mean(dim=0, keepdim=True)
     elif normalize == 'global':
@@ -110,7 +142,7 @@ def symmreg_i(x_fx, autoencoder, generator, f=None, dfdx=None, normalize='global
         x = x_fx[:, 0]
         loss = 0.0
         for v in generator.get_full_basis_list():
-            tangent = jvp_fn(autoencoder.decoder, z, v=_act_on_latent(v, z))[1]
+            tangent = _decoder_tangent(autoencoder, z, _act_on_latent(v, z), require_grad)
             v_x, v_fx = tangent[:, 0], tangent[:, 1]
             if isinstance(f, EulerFlowMap):
                 pushed = f.jvp(x, v_x, require_grad)[1]          # one fused launch instead of a double vjp
@@ -143,7 +175,7 @@ def symmreg_f(x_fx, autoencoder, generator, f, normalize='global', z_mean=None, 
         fx = x_fx[:, 1]
         loss = 0.0
         for g in generator.get_deterministic_group_elems():
-            moved = autoencoder.decode(_act_on_latent(g, z) + z_mean)
+            moved = _decode(autoencoder, _act_on_latent(g, z) + z_mean)
             g_x, g_fx = moved[:, 0], moved[:, 1]
             if numpy:
                 f_g_x = torch.from_numpy(f(g_x.cpu().numpy())).float().to(generator.Li[0].device)
@@ -158,7 +190,22 @@ def symmreg_f(x_fx, autoencoder, generator, f, normalize='global', z_mean=None, 
 def _group_transform(autoencoder, g, x, normalize='global', z_mean=None):
     """x -> decode(g·(encode(x) − centre) + centre), first component (reference `model_utils.py:145-158`)."""
     z, z_mean = _centred_latent(autoencoder, torch.stack([x, x], dim=1), normalize, z_mean)
-    return autoencoder.decode(_act_on_latent(g, z) + z_mean)[:, 0]
+    return _decode(autoencoder, _act_on_latent(g, z) + z_mean)[:, 0]
+
+
+def _group_transform_jvp(autoencoder, g, x, v, normalize, z_mean, require_grad):
+    """(g(x), J_g(x)·v) for the map of `_group_transform` (`model_utils.py:145-163`). With the tensor-core MLPs the
+    tangent is pushed through encoder, latent action and decoder in forward mode; otherwise the reference's double vjp."""
+    fast = _fast_ae(autoencoder, x)
+    if fast is None or normalize != 'global':         # 'in_batch': the batch mean couples the rows, keep autograd's graph
+        move = partial(_group_transform, autoencoder, g, normalize=normalize, z_mean=z_mean)
+        return move(x), _jvp_fn(require_grad)(move, x, v=v)[1]
+    enc, dec = fast
+    z, dz = enc.value_and_jvp(torch.stack([x, x], dim=1), torch.stack([v, v], dim=1))
+    if z_mean is None:
+        z_mean = autoencoder.encoder[-2].bias
+    moved, dmoved = dec.value_and_jvp(_act_on_latent(g, z - z_mean) + z_mean, _act_on_latent(g, dz))
+    return moved[:, 0], dmoved[:, 0]
 
 
 def symmreg_r(x, autoencoder, generator, h, normalize='global', z_mean=None, require_grad=False, scale=0.01):
@@ -169,9 +216,7 @@ def symmreg_r(x, autoencoder, generator, h, normalize='global', z_mean=None, req
     with torch.set_grad_enabled(require_grad):
         loss = 0.0
         for g in generator.get_deterministic_group_elems(scale=scale):
-            move = partial(_group_transform, autoencoder, g, normalize=normalize, z_mean=z_mean)
-            gx = move(x)
-            pushed = jvp_fn(move, x, v=h(x))[1]
+            gx, pushed = _group_transform_jvp(autoencoder, g, x, h(x), normalize, z_mean, require_grad)
             loss += torch.mean((pushed - h(gx)) ** 2)
     return loss
 
@@ -208,14 +253,13 @@ def group_action_and_jacobian(x, autoencoder, generator, z_mean=None, scale=0.01
     d = x.shape[-1]
     with torch.no_grad():
         for g in generator.get_deterministic_group_elems(scale=scale):
-            move = partial(_group_transform, autoencoder, g, normalize=normalize, z_mean=z_mean)
-            gx_list.append(move(x))
+            gx_list.append(_group_transform(autoencoder, g, x, normalize=normalize, z_mean=z_mean))
             cols = []
             for j in range(d):
                 e = torch.zeros_like(x)
                 e[:, j] = 1.0
                 with torch.enable_grad():
-                    cols.append(jvp(move, x, v=e)[1].detach())
+                    cols.append(_group_transform_jvp(autoencoder, g, x, e, normalize, z_mean, False)[1].detach())
             Jgx_list.append(torch.stack(cols, dim=-1))            # [b, a, j] = d g_a / d x_j
     return gx_list, Jgx_list
 

@@ -79,6 +79,15 @@ _SIGNATURES = {
                                        c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "sb_symreg_r": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, POINTER(_CLibrary), c_void_p, c_void_p, c_void_p,
                             c_int64, c_void_p]),
+    "sb_mlp_panel_bytes": (c_int64, [c_int64, c_int]),
+    "sb_mlp_pack_weights": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "sb_mlp_pack_rows": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "sb_mlp_unpack_rows": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "sb_mlp_thin_in": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
+                               c_void_p]),
+    "sb_mlp_thin_out": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "sb_mlp_gemm": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p,
+                            c_void_p]),
     "sb_debug_trace": (None, [c_void_p]),
     "sb_fp32_peak": (c_int, [c_int, c_int, POINTER(c_double), c_void_p]),
 }

@@ -454,3 +454,38 @@ def test_lie_derivative_matrix_is_the_jacobian_identity(d, p):
     M2 = symreg.lie_matrix(native.Library(d, p), torch.tensor(L)).numpy()
     np.testing.assert_allclose(th @ M1.T, lhs, rtol=2e-5, atol=2e-5)     # M1 is stored in fp32 like the reference's
     np.testing.assert_allclose(th @ M2.T, lhs, rtol=1e-10, atol=1e-10)
+
+
+def test_frozen_autoencoder_folding_reproduces_the_module():
+    """`sindy_b200.mlp.fold_layers` (host side of the tensor-core MLP chain, §8f-3): the Linear / BatchNorm(eval) / ReLU
+    tree of the reference's AutoEncoder (`autoencoder.py:38-66`) folded to plain (W, b) layers evaluates to the module's
+    own output; other module trees are refused."""
+    import torch
+    from sindy_b200 import mlp
+    from test_gpu_mlp import RefShapedAutoEncoder
+    torch.manual_seed(0)
+    ae = RefShapedAutoEncoder(hidden=64).double()
+    with torch.no_grad():
+        for m in ae.modules():
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.running_mean.normal_(0, 0.1); m.running_var.uniform_(0.5, 1.5)
+                m.weight.normal_(1.0, 0.2); m.bias.normal_(0, 0.1)
+    assert mlp.fold_layers(ae.encoder) is None                       # trainable parameters
+    for p in ae.parameters():
+        p.requires_grad_(False)
+    assert mlp.fold_layers(ae.encoder) is None                       # training mode: batch statistics
+    ae.eval()
+    x = torch.randn(37, 2, 2, dtype=torch.float64)
+    for mod in (ae.encoder, ae.decoder):
+        layers, out_shape = mlp.fold_layers(mod)
+        h = x.reshape(-1, 2)
+        for i, (w, b) in enumerate(layers):
+            h = h @ w.t() + b
+            if i + 1 < len(layers):
+                h = h.clamp_min(0)
+        want = mod(x)
+        assert out_shape in (None, (-1, 2, 2))
+        assert torch.allclose(h.reshape(want.shape), want, rtol=1e-12, atol=1e-13)
+    assert mlp.accelerate(ae) is None                                # CPU module: the PyTorch path stays
+    ae.decoder[1] = torch.nn.Tanh()
+    assert mlp.fold_layers(ae.decoder) is None

@@ -1,0 +1,226 @@
+"""GPU parity of the tensor-core MLP chain (`sindy_b200/mlp.py`, `csrc/sb_mlp.cu`) against plain PyTorch
+fp32 / fp64 evaluations of the same frozen network — the reference's `AutoEncoder` encoder / decoder structure
+(`autoencoder.py:38-66`: Linear + BatchNorm1d(eval) + ReLU blocks, orthogonal last encoder layer, 512 wide, 5 layers).
+Tolerance: with both halves of the split rounded to nearest the products carry ~22 mantissa bits; what remains is the
+tensor core's fp32 accumulator, which truncates on each of the 192 accumulations per output: measured 3.3e-6 of the
+largest output for one 512-deep layer against fp64 (cuBLAS fp32: 8e-7; one-pass TF32: 1e-3). Bounds: 1e-5 per layer,
+2e-5 through the five-layer networks and their derivatives."""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+from torch.nn.utils.parametrizations import orthogonal
+
+pytestmark = pytest.mark.gpu
+
+
+class Reshape(nn.Module):          # same name and behaviour as the reference's `model.py:8-14`
+    def __init__(self, *args):
+        super().__init__()
+        self.shape = args
+
+    def forward(self, x):
+        return x.reshape(self.shape)
+
+
+class RefShapedAutoEncoder(nn.Module):
+    """Module tree of `autoencoder.py:38-66` (ae_arch 'mlp', batch_norm, ortho_ae, activation ReLU)."""
+
+    def __init__(self, input_dim=2, hidden=512, latent=2, n_layers=5, n_comps=2):
+        super().__init__()
+        bn = lambda f: [Reshape(-1, f), nn.BatchNorm1d(f), Reshape(-1, n_comps, f)]
+        self.encoder = nn.Sequential(
+            nn.Linear(input_dim, hidden), *bn(hidden), nn.ReLU(),
+            *[nn.Sequential(nn.Linear(hidden, hidden), *bn(hidden), nn.ReLU()) for _ in range(n_layers - 1)],
+            orthogonal(nn.Linear(hidden, latent)), *bn(latent))
+        self.decoder = nn.Sequential(
+            nn.Linear(latent, hidden), nn.ReLU(),
+            *[nn.Sequential(nn.Linear(hidden, hidden), nn.ReLU()) for _ in range(n_layers - 1)],
+            nn.Linear(hidden, input_dim))
+
+    def encode(self, x):
+        return self.encoder(x)
+
+    def decode(self, z):
+        return self.decoder(z)
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+
+def make_ae(seed=0, **kw):
+    torch.manual_seed(seed)
+    ae = RefShapedAutoEncoder(**kw)
+    with torch.no_grad():
+        for m in ae.modules():
+            if isinstance(m, nn.BatchNorm1d):
+                m.running_mean.copy_(0.1 * torch.randn_like(m.running_mean))
+                m.running_var.copy_(0.5 + torch.rand_like(m.running_var))
+                m.weight.copy_(1.0 + 0.2 * torch.randn_like(m.weight))
+                m.bias.copy_(0.1 * torch.randn_like(m.bias))
+    ae.eval()
+    for p in ae.parameters():
+        p.requires_grad_(False)
+    return ae.cuda()
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def rel_rows(a, b, outliers=1e-2):
+    """Error of a DERIVATIVE of a ReLU network: a unit whose pre-activation is within rounding of zero flips its mask
+    and changes that row's Jacobian by O(1/sqrt(width)) in any fp32 evaluation (cuBLAS against fp64 as well). Rows are
+    therefore judged individually: the given fraction may be off, the rest is returned as a max-norm relative error."""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    err = (a - b).abs().reshape(a.shape[0], -1).max(dim=1).values / b.abs().max().clamp_min(1e-30)
+    k = 0 if err.numel() < 50 else max(2, int(outliers * err.numel()))
+    return float(err.sort().values[err.numel() - 1 - k])
+
+
+@pytest.fixture(scope="module")
+def mlp():
+    from sindy_b200 import mlp as M
+    assert torch.cuda.is_available()
+    return M
+
+
+@pytest.mark.parametrize("m", [1, 127, 128, 300, 4097])
+def test_panel_format_round_trip_is_exact(mlp, m):
+    x = torch.randn(m, 512, device="cuda") * torch.logspace(-6, 6, 512, device="cuda")
+    p = mlp._Panel.from_rows(x)
+    assert bool(((p.to_rows() - x).abs() <= x.abs() * 2.0 ** -23).all())   # hi + lo: two tf32 roundings, ≤ 2⁻²⁴ relative
+
+
+@pytest.mark.parametrize("m,mode", [(128, 0), (300, 1), (1000, 2), (40000, 1)])
+def test_wide_layer_kernel_vs_fp64(mlp, m, mode):
+    """One sb_mlp_gemm launch: C = epilogue(A·Wᵀ (+ b)) for the three epilogues, ragged last tile included."""
+    from sindy_b200 import native
+    g = torch.Generator(device="cuda").manual_seed(m + mode)
+    f = 512
+    a = torch.randn(m, f, device="cuda", generator=g)
+    w = torch.randn(f, f, device="cuda", generator=g) / f ** 0.5
+    b = torch.randn(f, device="cuda", generator=g)
+    r = torch.randn(m, f, device="cuda", generator=g)
+    lib = native.load()
+    pa, pr, pc = mlp._Panel.from_rows(a), mlp._Panel.from_rows(r), mlp._Panel(m, f, a.device)
+    pk = torch.empty(2 * f * f, device="cuda")
+    s = native._stream(a.device)
+    native._check(lib.sb_mlp_pack_weights(w.data_ptr(), f, f, 0, pk.data_ptr(), s), "pack")
+    native._check(lib.sb_mlp_gemm(pa.ptr(), m, f, pk.data_ptr(), f, b.data_ptr() if mode != 2 else None,
+                                  pr.ptr() if mode == 2 else None, mode, pc.ptr(), s), "gemm")
+    ref = a.double() @ w.double().t()
+    if mode != 2:
+        ref = ref + b.double()
+    if mode == 1:
+        ref = ref.clamp_min(0)
+    if mode == 2:
+        ref = ref * (r > 0)
+    got = pc.to_rows()
+    assert rel(got, ref) < 1e-5
+    # the transposed packing: C = A·W
+    native._check(lib.sb_mlp_pack_weights(w.data_ptr(), f, f, 1, pk.data_ptr(), s), "pack")
+    native._check(lib.sb_mlp_gemm(pa.ptr(), m, f, pk.data_ptr(), f, None, None, 0, pc.ptr(), s), "gemm")
+    assert rel(pc.to_rows(), a.double() @ w.double()) < 1e-5
+
+
+@pytest.mark.parametrize("batch", [1, 77, 20000])
+def test_frozen_mlp_value_jvp_and_gradients_vs_torch(mlp, batch):
+    ae = make_ae(seed=3)
+    pair = mlp.accelerate(ae)
+    assert pair is not None, "the reference-shaped autoencoder must be recognised"
+    enc, dec = pair
+    assert mlp.accelerate(ae) is pair             # cached on the module
+    g = torch.Generator(device="cuda").manual_seed(batch)
+    x = torch.randn(batch, 2, 2, device="cuda", generator=g)
+    t = torch.randn(batch, 2, 2, device="cuda", generator=g)
+    ae64 = make_ae(seed=3).double()
+    for fast, mod, mod64 in ((enc, ae.encoder, ae64.encoder), (dec, ae.decoder, ae64.decoder)):
+        y = fast.value(x)
+        assert y.shape == mod(x).shape
+        assert rel(y, mod64(x.double())) < 2e-5
+        y2, jt = fast.value_and_jvp(x, t)
+        _, jt64 = torch.autograd.functional.jvp(mod64, x.double(), t.double())
+        assert torch.equal(y2, y) and rel_rows(jt, jt64) < 2e-5
+        # gradients with respect to x and t of a scalar of (value, tangent): the transpose chains
+        xg, tg = x.clone().requires_grad_(True), t.clone().requires_grad_(True)
+        cy, cj = torch.randn_like(y), torch.randn_like(jt)
+        yy, jj = fast.value_and_jvp(xg, tg)
+        ((yy * cy).sum() + (jj * cj).sum()).backward()
+        x64, t64 = x.double().requires_grad_(True), t.double().requires_grad_(True)
+        y64, j64 = torch.autograd.functional.jvp(mod64, x64, t64, create_graph=True)
+        ((y64 * cy.double()).sum() + (j64 * cj.double()).sum()).backward()
+        assert rel_rows(xg.grad, x64.grad) < 2e-5 and rel_rows(tg.grad, t64.grad) < 2e-5
+        xg = x.clone().requires_grad_(True)
+        (fast.value(xg) * cy).sum().backward()
+        x64 = x.double().requires_grad_(True)
+        (mod64(x64) * cy.double()).sum().backward()
+        assert rel_rows(xg.grad, x64.grad) < 2e-5
+
+
+def test_modules_outside_the_supported_form_keep_the_pytorch_path(mlp):
+    ae = make_ae(seed=1)
+    ae.train()
+    assert mlp.accelerate(ae) is None                               # BatchNorm would use batch statistics
+    ae.eval()
+    next(ae.decoder.parameters()).requires_grad_(True)
+    assert mlp.accelerate(ae) is None                               # trainable: autograd must see the parameters
+    next(ae.decoder.parameters()).requires_grad_(False)
+    assert mlp.accelerate(ae) is not None
+    ae.decoder[1] = nn.Tanh()
+    assert mlp.accelerate(ae) is None                               # not piecewise linear
+    small = make_ae(seed=1, hidden=96)
+    assert mlp.accelerate(small) is None                            # width not a multiple of 256
+
+
+def test_weight_update_invalidates_the_cached_chain(mlp):
+    ae = make_ae(seed=2)
+    x = torch.randn(64, 2, 2, device="cuda")
+    y0 = mlp.accelerate(ae)[1].value(x)
+    with torch.no_grad():
+        ae.decoder[0].weight.mul_(1.5)
+    y1 = mlp.accelerate(ae)[1].value(x)
+    assert rel(y1, ae.decoder(x)) < 2e-5 and rel(y0, y1) > 1e-2
+
+
+def test_symmetry_regularisers_through_the_tensor_core_chain(mlp, monkeypatch):
+    """symmreg_i / symmreg_f / symmreg_r / group_action_and_jacobian with the autoencoder on the tensor cores against
+    the same functions on the PyTorch modules (SINDY_B200_AE_MLP=0): loss values and dL/dΞ."""
+    import model_utils
+    import sindy
+    import standins
+    ae = make_ae(seed=5)
+    _, gen = standins.make_standins(seed=0, input_dim=2, n_comps=2, hidden=32, device="cuda")
+    torch.manual_seed(0)
+    x = 0.5 * torch.randn(4000, 2, device="cuda")
+    reg = sindy.SINDyRegression(2, 2, False, True, threshold=0.05, device="cuda", constrain_constant=True)
+    reg.Xi.data = 0.3 * torch.randn_like(reg.Xi)
+
+    def run():
+        out = {}
+        flow = model_utils.EulerFlowMap(reg, 0.1, 0.01)
+        x_fx = torch.stack([x, flow(x)], dim=1)
+        li = model_utils.symmreg_i(x_fx, ae, gen, f=flow, require_grad=True)
+        reg.zero_grad(); li.backward()
+        out["i"] = (float(li), reg.Xi.grad.clone())
+        x_fx = torch.stack([x, flow(x)], dim=1)
+        lf = model_utils.symmreg_f(x_fx, ae, gen, f=flow, require_grad=True)
+        reg.zero_grad(); lf.backward()
+        out["f"] = (float(lf), reg.Xi.grad.clone())
+        lr = model_utils.symmreg_r(x, ae, gen, h=reg, require_grad=True)
+        reg.zero_grad(); lr.backward()
+        out["r"] = (float(lr), reg.Xi.grad.clone())
+        gx, jgx = model_utils.group_action_and_jacobian(x, ae, gen)
+        out["g"] = (torch.stack(gx), torch.stack(jgx))
+        return out
+
+    fast = run()
+    assert ae.__dict__.get("_sb_frozen_mlps", (None, None))[1] is not None
+    monkeypatch.setenv("SINDY_B200_AE_MLP", "0")
+    slow = run()
+    for k in "ifr":
+        assert abs(fast[k][0] - slow[k][0]) < 1e-4 * abs(slow[k][0]), k
+        assert rel(fast[k][1], slow[k][1]) < 5e-4, k
+    assert rel(fast["g"][0][0], slow["g"][0][0]) < 1e-5 and rel_rows(fast["g"][1][0], slow["g"][1][0]) < 1e-4

@@ -48,7 +48,8 @@ def closure(fused):
     return loss
 
 
-for fused in (False, True):
+for fused, ae_tc in ((False, False), (True, False), (True, True)):
+    os.environ["SINDY_B200_AE_MLP"] = "1" if ae_tc else "0"
     for _ in range(3):
         closure(fused)
     torch.cuda.synchronize()
@@ -63,7 +64,10 @@ for fused in (False, True):
     ev = [e for e in prof.key_averages() if e.device_time_total > 0 and e.device_type == torch.autograd.DeviceType.CUDA]
     tot = sum(e.device_time_total for e in ev)
     n_launch = sum(e.count for e in ev)
-    print(f"\n=== closure, {'fused Euler flow (EulerFlowMap)' if fused else 'closure + double vjp (reference call pattern)'}: "
+    what = ('fused Euler flow (EulerFlowMap)' if fused else 'closure + double vjp (reference call pattern)') + \
+        (' + autoencoder on the tensor cores (sb_mlp_gemm)' if ae_tc else '')
+    lv = closure(fused)
+    print(f"\n=== closure, {what}: loss {float(lv):.7f}, |grad| {float(reg.Xi.grad.norm()):.7f}, "
           f"B={B} wall {wall * 1e3:.2f} ms, GPU busy {tot / 1e3:.2f} ms in {n_launch} launches ===")
     for e in sorted(ev, key=lambda q: -q.device_time_total)[:12]:
         print(f"  {e.device_time_total / 1e3:8.3f} ms  x{e.count:4d}  {e.key[:100]}")
