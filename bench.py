@@ -796,6 +796,75 @@ def extras(native, dev, peaks, fp32_peak):
         del xs, vs, gs, gxs, Jg
     except Exception as exc:   # noqa: BLE001
         out["symreg_kernels_config3_library_1e7"] = {"error": repr(exc)}
+    # the frozen autoencoder of config 3 (`autoencoder.py:38-66`: 2 -> 512 x 5 -> 2, BatchNorm in the encoder, ReLU) on
+    # the tensor cores: one 512-wide layer (40 000 rows = 20 000 samples x 2 components) against cuBLAS
+    # fp32 through PyTorch, and the encoder value + decoder JVP + both transpose chains of `symmreg_i`'s closure against
+    # the reference's call pattern (module forward, double-vjp JVP, autograd backward) on the same module
+    try:
+        from sindy_b200 import mlp as _mlp
+        m_rows, f = 40000, 512
+        a = torch.randn(m_rows, f, device=dev, generator=gen)
+        wl = torch.randn(f, f, device=dev, generator=gen) / f ** 0.5
+        bl = torch.randn(f, device=dev, generator=gen)
+        pa, pc = _mlp._Panel.from_rows(a), _mlp._Panel(m_rows, f, dev)
+        pk = torch.empty(2 * f * f, device=dev)
+        sl = native.load()
+        native._check(sl.sb_mlp_pack_weights(wl.data_ptr(), f, f, 0, pk.data_ptr(), native._stream(dev)), "pack")
+        ms_tc = timed(lambda: native._check(sl.sb_mlp_gemm(pa.ptr(), m_rows, f, pk.data_ptr(), f, bl.data_ptr(), None, 1,
+                                                           pc.ptr(), native._stream(dev)), "gemm"), reps=20)
+        torch.backends.cuda.matmul.allow_tf32 = False
+        ms_cublas = timed(lambda: torch.relu(torch.nn.functional.linear(a, wl, bl)), reps=20)
+        ref64 = torch.relu(a.double() @ wl.double().t() + bl.double())
+        err_tc = float((pc.to_rows().double() - ref64).abs().max() / ref64.abs().max())
+        err_cublas = float((torch.relu(torch.nn.functional.linear(a, wl, bl)).double() - ref64).abs().max() / ref64.abs().max())
+        fl = 2.0 * m_rows * f * f
+        peak_tf32 = peaks.get("bf16_tflops", 0.0) / 2.0
+        layer = {"ms": ms_tc, "fp32_equivalent_tflops": fl / (ms_tc * 1e-3) / 1e12,
+                 "tf32_mma_tflops_issued": 3 * fl / (ms_tc * 1e-3) / 1e12,
+                 "frac_of_tf32_peak": (3 * fl / (ms_tc * 1e-3) / 1e12 / peak_tf32) if peak_tf32 else None,
+                 "tf32_peak_tflops": peak_tf32, "tf32_peak_source": "half of MEASURED_PEAKS dense bf16 (cuBLAS)",
+                 "max_err_vs_fp64": err_tc, "cublas_fp32_ms": ms_cublas, "cublas_fp32_max_err_vs_fp64": err_cublas,
+                 "speedup_vs_cublas_fp32": ms_cublas / ms_tc,
+                 "hbm_gbs": 2 * 8 * m_rows * f / (ms_tc * 1e-3) / 1e9}
+        del a, pa, pc, ref64
+
+        def bn_block(i, o):
+            return [torch.nn.Linear(i, o), torch.nn.BatchNorm1d(o), torch.nn.ReLU()]
+        torch.manual_seed(0)
+        enc = torch.nn.Sequential(*bn_block(2, f), *[q for _ in range(4) for q in bn_block(f, f)], torch.nn.Linear(f, 2))
+        dec = torch.nn.Sequential(torch.nn.Linear(2, f), torch.nn.ReLU(),
+                                  *[q for _ in range(4) for q in (torch.nn.Linear(f, f), torch.nn.ReLU())],
+                                  torch.nn.Linear(f, 2))
+        for mod in (enc, dec):
+            mod.to(dev).eval()
+            for q in mod.parameters():
+                q.requires_grad_(False)
+        fe, fd = _mlp.FrozenMLP.from_module(enc), _mlp.FrozenMLP.from_module(dec)
+        xb = torch.randn(m_rows, 2, device=dev, generator=gen)
+        cb = torch.randn(m_rows, 2, device=dev, generator=gen)
+        gmat = torch.randn(2, 2, device=dev, generator=gen)
+
+        def chain(encode, dec_tangent):
+            xg = xb.clone().requires_grad_(True)
+            z = encode(xg)
+            (dec_tangent(z, z @ gmat) * cb).sum().backward()
+            return xg.grad
+
+        ours = lambda: chain(fe.value, lambda z, v: fd.value_and_jvp(z, v)[1])
+        theirs = lambda: chain(enc, lambda z, v: torch.autograd.functional.jvp(dec, z, v, create_graph=True)[1])
+        ms_o, ms_t = timed(ours, reps=10), timed(theirs, reps=10)
+        d_rows = (ours() - theirs()).abs().max(dim=1).values / theirs().abs().max()
+        out["autoencoder_mlp_config3_40000rows"] = {
+            "layer_512x512_sb_mlp_gemm": layer,
+            "symmreg_i_autoencoder_part": {"tensor_core_chain_ms": ms_o, "pytorch_double_vjp_ms": ms_t,
+                                           "speedup": ms_t / ms_o, "gemm_launches": 20,
+                                           "median_rel_diff": float(d_rows.median()),
+                                           "rows_above_1e-5": int((d_rows > 1e-5).sum()),
+                                           "note": "rows differ where a ReLU unit sits within rounding of zero"},
+            "kernel": "mlp_gemm_kernel (tcgen05 kind::tf32, 3xTF32, split accumulators, panel-format operands by bulk copy)"}
+        del xb, cb
+    except Exception as exc:   # noqa: BLE001
+        out["autoencoder_mlp_config3_40000rows"] = {"error": repr(exc)}
     # WSINDy weak-form integrals over MANY trajectories: batches of Sel'kov-shaped trajectories
     # (T = 8000, 50 test functions) for the config-4 library and for the C5 library; algorithmic cost per time sample
     # (K−1−d) + 2·n_test·(K+d) flop (test functions are generated once per time tile for the whole batch) and 4·d bytes

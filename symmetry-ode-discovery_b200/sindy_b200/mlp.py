@@ -292,14 +292,18 @@ class _ValueJvp(Function):
         hs, y = mlp._value_chain(rows, keep=True)
         jt = mlp._tangent_chain(trows, hs)
         ctx.mlp, ctx.hs = mlp, hs
+        ctx.set_materialize_grads(False)      # an unused output (symmreg_i takes only the tangent) costs no chain
         return y, jt
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, gy, gjt):
         # d(J(x)·t)/dx vanishes almost everywhere for ReLU networks (the reference's autograd returns the same zeros)
-        gx = ctx.mlp._transpose_chain(native._f32c(gy, "gy"), ctx.hs) if ctx.needs_input_grad[0] else None
-        gt = ctx.mlp._transpose_chain(native._f32c(gjt, "gjt"), ctx.hs) if ctx.needs_input_grad[1] else None
+        gx = gt = None
+        if ctx.needs_input_grad[0] and gy is not None:
+            gx = ctx.mlp._transpose_chain(native._f32c(gy, "gy"), ctx.hs)
+        if ctx.needs_input_grad[1] and gjt is not None:
+            gt = ctx.mlp._transpose_chain(native._f32c(gjt, "gjt"), ctx.hs)
         return gx, gt, None
 
 
