@@ -51,7 +51,17 @@ struct GemmArgs {
   const unsigned char* R;   // panel format like C: mask source (kMask)
   unsigned char* C;         // panel format, m_tiles × (n_tiles·16) blocks
   int m_tiles, k_blocks, n_tiles, mode;
+  int full_tiles, split, items;   // one-CTA kernel: work items = full 128×256 tiles, then the last partial round as
+                                  // `split` narrower pieces per tile (128 × 256/split) so that it fills the SMs
 };
+
+struct Piece { int mt, nt, n0, bn; };
+__device__ __forceinline__ Piece decode_item(int t, const GemmArgs& a) {
+  if (t < a.full_tiles) return Piece{t / a.n_tiles, t % a.n_tiles, 0, kBN};
+  const int u = t - a.full_tiles;
+  const int tile = a.full_tiles + u / a.split, bn = kBN / a.split;
+  return Piece{tile / a.n_tiles, tile % a.n_tiles, (u % a.split) * bn, bn};
+}
 
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
   // SmemDescriptor (cute/arch/mma_sm100_desc.hpp): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48),
@@ -63,11 +73,12 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
 constexpr uint32_t kIdesc =
     (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
 
-__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate,
+                                         uint32_t idesc = kIdesc) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(da), "l"(db), "r"(kIdesc), "r"(accumulate)
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
@@ -138,24 +149,30 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_gemm_kernel(GemmArgs a) {
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = tmem_base_s;
-  const int n_tiles_total = a.m_tiles * a.n_tiles;
   const int KB = a.k_blocks;
 
   if (wid == 0) {
     // ===== bulk-copy producer =====
     if (lane == 0) {
       uint32_t it = 0;
-      for (int t = blockIdx.x; t < n_tiles_total; t += gridDim.x) {
-        const int mt = t / a.n_tiles, nt = t % a.n_tiles;
-        const unsigned char* Ap = a.A + (size_t)mt * KB * (2 * kABlock);
-        const unsigned char* Wp = a.W + (size_t)nt * KB * (2 * kBBlock);
+      for (int t = blockIdx.x; t < a.items; t += gridDim.x) {
+        const Piece pc = decode_item(t, a);
+        const unsigned char* Ap = a.A + (size_t)pc.mt * KB * (2 * kABlock);
+        // rows [n0, n0 + bn) of a weight block half are contiguous: (n0/8) row groups of 512 B in
+        const unsigned char* Wp = a.W + (size_t)pc.nt * KB * (2 * kBBlock) + (size_t)pc.n0 * (kBK * 4);
+        const uint32_t b_bytes = (uint32_t)pc.bn * (kBK * 4);
         for (int kb = 0; kb < KB; ++kb, ++it) {
           const uint32_t s = it % kStages;
           if (it >= kStages) mbar_wait(&empty[s], ((it / kStages) - 1) & 1u);
           unsigned char* st = base + (size_t)s * kStageBytes;
-          mbar_expect_tx(&full[s], kStageBytes);
+          mbar_expect_tx(&full[s], 2 * kABlock + 2 * b_bytes);
           tma_load_1d(st, Ap + (size_t)kb * (2 * kABlock), 2 * kABlock, &full[s]);
-          tma_load_1d(st + 2 * kABlock, Wp + (size_t)kb * (2 * kBBlock), 2 * kBBlock, &full[s]);
+          if (pc.bn == kBN) {
+            tma_load_1d(st + 2 * kABlock, Wp + (size_t)kb * (2 * kBBlock), 2 * kBBlock, &full[s]);
+          } else {
+            tma_load_1d(st + 2 * kABlock, Wp + (size_t)kb * (2 * kBBlock), b_bytes, &full[s]);
+            tma_load_1d(st + 2 * kABlock + kBBlock, Wp + (size_t)kb * (2 * kBBlock) + kBBlock, b_bytes, &full[s]);
+          }
         }
       }
     }
@@ -164,7 +181,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_gemm_kernel(GemmArgs a) {
     if (lane == 0) {
       uint32_t it = 0, lt = 0;
       const uint64_t desc0 = umma_desc(smem_u32(base));   // later stages: the start-address field (bytes >> 4) moves
-      for (int t = blockIdx.x; t < n_tiles_total; t += gridDim.x, ++lt) {
+      for (int t = blockIdx.x; t < a.items; t += gridDim.x, ++lt) {
+        const uint32_t idesc = (kIdesc & ~(0x3Fu << 17)) | ((uint32_t)(decode_item(t, a).bn >> 3) << 17);
         const uint32_t buf = lt % kBufs;
         if (lt >= kBufs) mbar_wait(&acc_empty[buf], ((lt / kBufs) - 1) & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -181,9 +199,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_gemm_kernel(GemmArgs a) {
             const uint64_t a_hi = d0 + (adv >> 4), a_lo = d0 + ((kABlock + adv) >> 4);
             const uint64_t b_hi = d0 + ((2 * kABlock + adv) >> 4), b_lo = d0 + ((2 * kABlock + kBBlock + adv) >> 4);
             const uint32_t acc = (kb > 0 || ks > 0) ? 1u : 0u;
-            mma_tf32(s_addr, a_lo, b_hi, acc);                          // small terms first
-            mma_tf32(s_addr, a_hi, b_lo, 1u);
-            mma_tf32(d_addr, a_hi, b_hi, SPLIT ? acc : 1u);
+            mma_tf32(s_addr, a_lo, b_hi, acc, idesc);                   // small terms first
+            mma_tf32(s_addr, a_hi, b_lo, 1u, idesc);
+            mma_tf32(d_addr, a_hi, b_hi, SPLIT ? acc : 1u, idesc);
           }
           mma_commit(&empty[s]);
         }
@@ -197,17 +215,20 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_gemm_kernel(GemmArgs a) {
     const int row = 32 * q + lane;
     const uint32_t row_off = blk_off(row, 0);
     uint32_t lt = 0;
-    for (int t = blockIdx.x; t < n_tiles_total; t += gridDim.x, ++lt) {
-      const int mt = t / a.n_tiles, nt = t % a.n_tiles;
+    for (int t = blockIdx.x; t < a.items; t += gridDim.x, ++lt) {
+      const Piece pc = decode_item(t, a);
       const uint32_t buf = lt % kBufs;
       mbar_wait(&acc_full[buf], (lt / kBufs) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const size_t panel = ((size_t)mt * a.n_tiles * (kBN / kBK) + (size_t)nt * (kBN / kBK)) * (2 * kABlock);
+      // accumulator column c of a piece is output feature nt·256 + n0 + c
+      const size_t panel = ((size_t)pc.mt * a.n_tiles * (kBN / kBK) + (size_t)pc.nt * (kBN / kBK) + (size_t)(pc.n0 / kBK)) *
+                           (2 * kABlock);
       unsigned char* Cp = a.C + panel;
       const unsigned char* Rp = a.R ? a.R + panel : nullptr;
-      const float* bias = a.bias ? a.bias + nt * kBN : nullptr;
+      const float* bias = a.bias ? a.bias + pc.nt * kBN + pc.n0 : nullptr;
+      const int col_hi = col_lo + kBN / (kEpiWarps / 4) < pc.bn ? col_lo + kBN / (kEpiWarps / 4) : pc.bn;
 #pragma unroll 1
-      for (int c0 = col_lo; c0 < col_lo + kBN / (kEpiWarps / 4); c0 += 16) {
+      for (int c0 = col_lo; c0 < col_hi; c0 += 16) {
         uint32_t r[16];
         tmem_ld16(tmem_d + ((uint32_t)(32 * q) << 16) + buf * (uint32_t)kBN + (uint32_t)c0, r);
         float v[16];
@@ -252,6 +273,218 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_gemm_kernel(GemmArgs a) {
   if (wid == 1) {
     __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(kTmemCols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (`cta_group::2`): the two SMs of a TPC compute one 256 × 256 tile. Each CTA stages ITS 128 rows of A
+// and ITS 128-row half of the weight block; the pair's tensor cores read both halves of B, so a CTA's shared-memory pipe
+// carries 3·(4+4) KB of operand reads + 16 KB of bulk-copy writes per 8-deep step (104 B/clk) instead of 3·(4+8) + 24
+// (156 B/clk of a 128 B/clk pipe: the limit ncu named for the one-CTA kernel). Rank 0 issues the MMAs; rank 1's MMA
+// warp relays "my stage landed" to rank 0's barrier (plain bulk copies cannot signal a peer's mbarrier); commits are
+// multicast to both CTAs; the epilogue warps of both CTAs drain their own TMEM and release rank 0's accumulator barrier.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kStages2 = 6;
+constexpr uint32_t kBHalf = kBBlock / 2;                              // 8 KB: 128 of the 256 weight rows, hi or lo
+constexpr uint32_t kStageBytes2 = 2 * kABlock + 2 * kBHalf;           // 32 KB
+constexpr size_t kSmem2 = 1024 + (size_t)kStages2 * kStageBytes2 + 256;
+constexpr uint32_t kIdesc2 =
+    (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(cta)
+      : "memory");
+}
+// Waits use the default (CTA-scope acquire) form: what crosses the pair is consumed by the tensor core through the async
+// proxy or is TMEM, never generic loads of the waiting thread. A cluster-scope acquire compiles to TRYWAIT + CCTL.IVALL —
+// an L1 invalidation per stage on the MMA-issuing thread — and measured 0.150 ms per layer against 0.109 for one CTA.
+__device__ __forceinline__ void mma_tf32_pair(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(kIdesc2), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+      : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_gemm_pair_kernel(GemmArgs a) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)kStages2 * kStageBytes2);
+  uint64_t* full = bars;                      // [kStages2] this CTA's copies landed (+ on rank 0: the peer's relay)
+  uint64_t* empty = bars + kStages2;          // [kStages2] the stage's MMAs retired (multicast commit)
+  uint64_t* acc_full = bars + 2 * kStages2;   // accumulators complete (multicast commit)
+  uint64_t* acc_empty = acc_full + 1;         // rank 0: accumulators drained by the epilogue warps of BOTH CTAs
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  if (tid == 0) {
+    for (int s = 0; s < kStages2; ++s) { mbar_init(&full[s], rank == 0 ? 2 : 1); mbar_init(&empty[s], 1); }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 2 * kEpiWarps);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  if (wid == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();                          // both CTAs' barriers exist before any remote arrive / multicast commit
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = tmem_base_s;
+  const int m_pairs = (a.m_tiles + 1) >> 1;
+  const int n_tiles_total = m_pairs * a.n_tiles;
+  const int KB = a.k_blocks;
+
+  if (wid == 0) {
+    // ===== bulk-copy producer (both CTAs: own A rows, own half of the weight rows) =====
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = pair; t < n_tiles_total; t += n_pairs) {
+        const int mp = t / a.n_tiles, nt = t % a.n_tiles;
+        int mt = 2 * mp + (int)rank;
+        if (mt >= a.m_tiles) mt = a.m_tiles - 1;                       // odd tile count: the idle half re-reads valid rows
+        const unsigned char* Ap = a.A + (size_t)mt * KB * (2 * kABlock);
+        const unsigned char* Wp = a.W + (size_t)nt * KB * (2 * kBBlock) + (size_t)rank * kBHalf;
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const uint32_t s = it % kStages2;
+          if (it >= kStages2) mbar_wait(&empty[s], ((it / kStages2) - 1) & 1u);
+          unsigned char* st = base + (size_t)s * kStageBytes2;
+          mbar_expect_tx(&full[s], kStageBytes2);
+          tma_load_1d(st, Ap + (size_t)kb * (2 * kABlock), 2 * kABlock, &full[s]);
+          tma_load_1d(st + 2 * kABlock, Wp + (size_t)kb * (2 * kBBlock), kBHalf, &full[s]);
+          tma_load_1d(st + 2 * kABlock + kBHalf, Wp + (size_t)kb * (2 * kBBlock) + kBBlock, kBHalf, &full[s]);
+        }
+      }
+    }
+  } else if (wid == 1) {
+    if (lane == 0 && rank == 1) {
+      // ===== relay: tell rank 0 that this CTA's half of the stage has landed =====
+      uint32_t it = 0;
+      for (int t = pair; t < n_tiles_total; t += n_pairs)
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const uint32_t s = it % kStages2;
+          mbar_wait(&full[s], (it / kStages2) & 1u);
+          mbar_arrive_remote(&full[s], 0);
+        }
+    } else if (lane == 0) {
+      // ===== MMA issuer (rank 0) =====
+      uint32_t it = 0, lt = 0;
+      const uint64_t desc0 = umma_desc(smem_u32(base));
+      const uint32_t d_addr = tmem_d, s_addr = tmem_d + (uint32_t)kBN;
+      for (int t = pair; t < n_tiles_total; t += n_pairs, ++lt) {
+        if (lt >= 1) mbar_wait(acc_empty, (lt - 1) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const uint32_t s = it % kStages2;
+          mbar_wait(&full[s], (it / kStages2) & 1u);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t d0 = desc0 + (uint64_t)(s * (kStageBytes2 >> 4));
+#pragma unroll
+          for (int ks = 0; ks < kBK / 8; ++ks) {
+            const uint32_t adv = (uint32_t)ks * 2u * kLBO;
+            const uint64_t a_hi = d0 + (adv >> 4), a_lo = d0 + ((kABlock + adv) >> 4);
+            const uint64_t b_hi = d0 + ((2 * kABlock + adv) >> 4), b_lo = d0 + ((2 * kABlock + kBHalf + adv) >> 4);
+            const uint32_t acc = (kb > 0 || ks > 0) ? 1u : 0u;
+            mma_tf32_pair(s_addr, a_lo, b_hi, acc);
+            mma_tf32_pair(s_addr, a_hi, b_lo, 1u);
+            mma_tf32_pair(d_addr, a_hi, b_hi, acc);
+          }
+          mma_commit_pair(&empty[s]);
+        }
+        mma_commit_pair(acc_full);
+      }
+    }
+  } else {
+    // ===== epilogue (both CTAs, own 128 rows) =====
+    const int q = wid & 3;
+    const int col_lo = ((wid - 2) >> 2) * (kBN / (kEpiWarps / 4));
+    const int row = 32 * q + lane;
+    const uint32_t row_off = blk_off(row, 0);
+    uint32_t lt = 0;
+    for (int t = pair; t < n_tiles_total; t += n_pairs, ++lt) {
+      const int mp = t / a.n_tiles, nt = t % a.n_tiles;
+      const int mt = 2 * mp + (int)rank;
+      const bool live = mt < a.m_tiles;
+      mbar_wait(acc_full, lt & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const size_t panel = ((size_t)(live ? mt : 0) * a.n_tiles * (kBN / kBK) + (size_t)nt * (kBN / kBK)) * (2 * kABlock);
+      unsigned char* Cp = a.C + panel;
+      const unsigned char* Rp = a.R ? a.R + panel : nullptr;
+      const float* bias = a.bias ? a.bias + nt * kBN : nullptr;
+      if (live) {
+#pragma unroll 1
+        for (int c0 = col_lo; c0 < col_lo + kBN / (kEpiWarps / 4); c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)c0, r);
+          float v[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]);
+          tmem_ld16(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)kBN + (uint32_t)c0, r);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] += __uint_as_float(r[e]);
+          const size_t blk = (size_t)(c0 / kBK) * (2 * kABlock);
+          if (bias) {
+#pragma unroll
+            for (int e4 = 0; e4 < 4; ++e4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c0) + e4);
+              v[4 * e4] += b4.x; v[4 * e4 + 1] += b4.y; v[4 * e4 + 2] += b4.z; v[4 * e4 + 3] += b4.w;
+            }
+          }
+          if (a.mode == kRelu) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.f);
+          } else if (a.mode == kMask) {
+#pragma unroll
+            for (int e4 = 0; e4 < 4; ++e4) {
+              const float4 m4 = __ldg(reinterpret_cast<const float4*>(Rp + blk + row_off + e4 * kLBO));
+              v[4 * e4] = m4.x > 0.f ? v[4 * e4] : 0.f;
+              v[4 * e4 + 1] = m4.y > 0.f ? v[4 * e4 + 1] : 0.f;
+              v[4 * e4 + 2] = m4.z > 0.f ? v[4 * e4 + 2] : 0.f;
+              v[4 * e4 + 3] = m4.w > 0.f ? v[4 * e4 + 3] : 0.f;
+            }
+          }
+#pragma unroll
+          for (int e4 = 0; e4 < 4; ++e4)
+            store_split(Cp + blk, kABlock, row_off + e4 * kLBO, v[4 * e4], v[4 * e4 + 1], v[4 * e4 + 2], v[4 * e4 + 3]);
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(acc_empty);
+        else mbar_arrive_remote(acc_empty, 0);
+      }
+    }
+  }
+  __syncthreads();
+  cluster_sync_all();                          // no CTA leaves while its partner may still read its shared memory
+  if (wid == 1) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(kTmemCols) : "memory");
   }
 }
 
@@ -454,13 +687,19 @@ int mlp_gemm(const void* a_panel, int64_t m, int k, const void* w_packed, int n,
   if ((m + 127) / 128 * (n / kBN) > (int64_t)1 << 30) { set_error("sb_mlp_gemm: too many rows"); return SB_ERR_INVALID; }
   static bool attr_set[64] = {false};
   static int sm_count[64] = {0};
-  static const bool split = [] { const char* e = getenv("SB_MLP_SPLIT_ACC"); return !(e && e[0] == '0'); }();
+  const char* es = getenv("SB_MLP_SPLIT_ACC");
+  const bool split = !(es && es[0] == '0');
+  const char* ep = getenv("SB_MLP_PAIR");          // A/B switches, read per call (tests flip them)
+  const bool pairs = ep && ep[0] == '1';
+  const char* en = getenv("SB_MLP_NARROW");
+  const bool no_narrow = en && en[0] == '0';
   int dev = 0;
   SB_CUDA_TRY(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64) { set_error("sb_mlp_gemm: device index %d", dev); return SB_ERR_INVALID; }
   if (!attr_set[dev]) {
     SB_CUDA_TRY(cudaFuncSetAttribute(mlp_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
     SB_CUDA_TRY(cudaFuncSetAttribute(mlp_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
+    SB_CUDA_TRY(cudaFuncSetAttribute(mlp_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem2));
     SB_CUDA_TRY(cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
     attr_set[dev] = true;
   }
@@ -468,8 +707,23 @@ int mlp_gemm(const void* a_panel, int64_t m, int k, const void* w_packed, int n,
   a.A = (const unsigned char*)a_panel; a.W = (const unsigned char*)w_packed; a.bias = bias;
   a.R = (const unsigned char*)mask_panel; a.C = (unsigned char*)c_panel;
   a.m_tiles = (int)((m + 127) / 128); a.k_blocks = k / kBK; a.n_tiles = n / kBN; a.mode = mode;
+  if (pairs) {
+    const int tiles2 = ((a.m_tiles + 1) / 2) * a.n_tiles;
+    const int max_pairs = sm_count[dev] / 2;
+    const int grid2 = 2 * (tiles2 < max_pairs ? tiles2 : max_pairs);
+    mlp_gemm_pair_kernel<<<grid2, kThreads, kSmem2, s>>>(a);
+    SB_LAUNCH_CHECK("mlp_gemm_pair_kernel");
+    return SB_OK;
+  }
   const int tiles = a.m_tiles * a.n_tiles;
-  const int grid = tiles < sm_count[dev] ? tiles : sm_count[dev];
+  // the last partial round (626 tiles on 148 SMs = 4 rounds + 34 tiles) as narrower pieces that fill the machine
+  const int sms = sm_count[dev];
+  const int rem = tiles % sms;
+  a.full_tiles = tiles - rem;
+  a.split = 1;
+  if (rem > 0 && !no_narrow) a.split = sms / rem >= 4 ? 4 : sms / rem >= 2 ? 2 : 1;
+  a.items = a.full_tiles + rem * a.split;
+  const int grid = a.items < sms ? a.items : sms;
   if (split) mlp_gemm_kernel<true><<<grid, kThreads, kSmem, s>>>(a);
   else mlp_gemm_kernel<false><<<grid, kThreads, kSmem, s>>>(a);
   SB_LAUNCH_CHECK("mlp_gemm_kernel");

@@ -94,10 +94,21 @@ def test_panel_format_round_trip_is_exact(mlp, m):
     assert bool(((p.to_rows() - x).abs() <= x.abs() * 2.0 ** -23).all())   # hi + lo: two tf32 roundings, ≤ 2⁻²⁴ relative
 
 
-@pytest.mark.parametrize("m,mode", [(128, 0), (300, 1), (1000, 2), (40000, 1)])
-def test_wide_layer_kernel_vs_fp64(mlp, m, mode):
-    """One sb_mlp_gemm launch: C = epilogue(A·Wᵀ (+ b)) for the three epilogues, ragged last tile included."""
+@pytest.mark.parametrize("variant", ["default", "no_narrow", "pair", "one_accumulator"])
+@pytest.mark.parametrize("m,mode", [(128, 0), (300, 1), (1000, 2), (2500, 1), (5100, 0), (40000, 1)])
+def test_wide_layer_kernel_vs_fp64(mlp, m, mode, variant, monkeypatch):
+    """One sb_mlp_gemm launch: C = epilogue(A·Wᵀ (+ b)) for the three epilogues, ragged last tile included. The row
+    counts exercise the last partial round as 4 narrow pieces per tile (128, 300, 1000, 40000), as 2 (2500) and whole
+    (5100); variants: all rounds whole tiles, the CTA-pair kernel (cta_group::2), one accumulator (A/B record)."""
     from sindy_b200 import native
+    if variant == "no_narrow":
+        monkeypatch.setenv("SB_MLP_NARROW", "0")
+    elif variant == "pair":
+        monkeypatch.setenv("SB_MLP_PAIR", "1")
+    elif variant == "one_accumulator":
+        if m != 40000:
+            pytest.skip("A/B variant: one size")
+        monkeypatch.setenv("SB_MLP_SPLIT_ACC", "0")
     g = torch.Generator(device="cuda").manual_seed(m + mode)
     f = 512
     a = torch.randn(m, f, device="cuda", generator=g)
