@@ -73,10 +73,15 @@ class EulerFlowMap:
 
 def _fast_ae(autoencoder, x):
     """(encoder, decoder) on the tensor cores (`sindy_b200.mlp.FrozenMLP`) when the autoencoder is the reference's MLP,
-    frozen, in eval mode and x lives on the GPU; None keeps the PyTorch modules. SINDY_B200_AE_MLP=0 switches it off."""
-    if not (torch.is_tensor(x) and x.is_cuda) or os.environ.get("SINDY_B200_AE_MLP", "1") == "0":
+    frozen, in eval mode and x lives on the GPU; None keeps the PyTorch modules. SINDY_B200_AE_MLP=0 switches it off,
+    =require raises instead of falling back."""
+    mode = os.environ.get("SINDY_B200_AE_MLP", "1")
+    if not (torch.is_tensor(x) and x.is_cuda) or mode == "0":
         return None
-    return _mlp.accelerate(autoencoder)
+    pair = _mlp.accelerate(autoencoder)
+    if pair is None and mode == "require":          # tests: prove that the tensor-core path is the one that ran
+        raise RuntimeError("SINDY_B200_AE_MLP=require: this autoencoder is not served by sindy_b200.mlp.FrozenMLP")
+    return pair
 
 
 def _encode(autoencoder, x):

@@ -60,11 +60,15 @@ def test_config1_with_the_references_own_train_loop(golden, tmp_path):
 
 @needs_ref
 def test_config3_lbfgs_with_symmreg_i_and_exp_library(golden, tmp_path):
-    """C3 `lv/noise99_eq_isymreg.cfg`: LBFGS + symmreg_i (10 Euler steps, double-vjp through the frozen 512x5
-    autoencoder) + (2, 2, exp) library, 27 epochs to the reference's "final convergence". The sym-reg term is a ratio of
+    """C3 `lv/noise99_eq_isymreg.cfg`: LBFGS + symmreg_i (10 Euler steps and their JVP in one fused launch, the frozen
+    512x5 autoencoder's value / JVP / transpose chains on the tensor cores) + (2, 2, exp) library, 27 epochs to the
+    reference's "final convergence". The sym-reg term is a ratio of
     two means through a random frozen MLP and LBFGS amplifies fp32 summation-order differences over ~500 closure
     evaluations: identical mask required, coefficients to 2e-3 of the largest."""
-    res, _ = config_runs.run_entry("C3", str(tmp_path), REF, dropin=True, gpu=0, env=ENV, timeout=3000)
+    # SINDY_B200_AE_MLP=require: the reference's own AutoEncoder class (loaded from the stand-in checkpoint, frozen by
+    # --fix_laligan) must be served by the tensor-core MLP chain (sb_mlp_gemm), not by a PyTorch fallback
+    res, _ = config_runs.run_entry("C3", str(tmp_path), REF, dropin=True, gpu=0,
+                                   env=dict(ENV, SINDY_B200_AE_MLP="require"), timeout=3000)
     err = _compare("C3", res, golden, 2e-3)
     print(f"C3: max coefficient error {err:.2e}")
 

@@ -235,3 +235,56 @@ def test_symmetry_regularisers_through_the_tensor_core_chain(mlp, monkeypatch):
         assert abs(fast[k][0] - slow[k][0]) < 1e-4 * abs(slow[k][0]), k
         assert rel(fast[k][1], slow[k][1]) < 5e-4, k
     assert rel(fast["g"][0][0], slow["g"][0][0]) < 1e-5 and rel_rows(fast["g"][1][0], slow["g"][1][0]) < 1e-4
+
+
+@pytest.mark.parametrize("variant", ["default", "no_narrow", "pair"])
+def test_layer_kernels_write_inside_their_buffers(mlp, variant, monkeypatch):
+    """Guard bands around every output buffer of the layer kernels (compute-sanitizer is not available on the GPU
+    pool): panel outputs of sb_mlp_pack_rows / thin_in / gemm and the row-major outputs of thin_out / unpack_rows sit
+    between sentinel regions that must come back untouched, for a ragged row count (300 = 2 tiles + 44 rows)."""
+    from sindy_b200 import native
+    if variant == "no_narrow":
+        monkeypatch.setenv("SB_MLP_NARROW", "0")
+    elif variant == "pair":
+        monkeypatch.setenv("SB_MLP_PAIR", "1")
+    lib = native.load()
+    dev = torch.device("cuda")
+    s = native._stream(dev)
+    m, f, guard = 300, 512, 1 << 14                       # guard: floats on either side
+    sentinel = -12345.678
+
+    def guarded(n_floats):
+        big = torch.full((n_floats + 2 * guard,), sentinel, device=dev)
+        return big, big[guard:guard + n_floats]
+
+    def intact(big, n_floats):
+        return bool((big[:guard] == sentinel).all()) and bool((big[guard + n_floats:] == sentinel).all())
+
+    n_panel = int(lib.sb_mlp_panel_bytes(m, f)) // 4
+    g = torch.Generator(device=dev).manual_seed(0)
+    x2 = torch.randn(m, 2, device=dev, generator=g)
+    w_in, b_in = torch.randn(f, 2, device=dev, generator=g), torch.randn(f, device=dev, generator=g)
+    w = torch.randn(f, f, device=dev, generator=g) / f ** 0.5
+    w_out = torch.randn(2, f, device=dev, generator=g)
+    big_a, pa = guarded(n_panel)
+    big_c, pc = guarded(n_panel)
+    big_y, y = guarded(m * 2)
+    big_r, rows = guarded(m * f)
+    pk = torch.empty(2 * f * f, device=dev)
+    native._check(lib.sb_mlp_pack_weights(w.data_ptr(), f, f, 0, pk.data_ptr(), s), "pack")
+    native._check(lib.sb_mlp_thin_in(x2.data_ptr(), m, 2, w_in.data_ptr(), b_in.data_ptr(), None, f, 1, pa.data_ptr(), s),
+                  "thin_in")
+    for mode, bias, mask in ((1, b_in, None), (2, None, pa), (0, None, None)):
+        native._check(lib.sb_mlp_gemm(pa.data_ptr(), m, f, pk.data_ptr(), f, bias.data_ptr() if bias is not None else None,
+                                      mask.data_ptr() if mask is not None else None, mode, pc.data_ptr(), s), "gemm")
+    native._check(lib.sb_mlp_thin_out(pc.data_ptr(), m, f, w_out.data_ptr(), None, 2, y.data_ptr(), s), "thin_out")
+    native._check(lib.sb_mlp_unpack_rows(pc.data_ptr(), m, f, rows.data_ptr(), s), "unpack")
+    torch.cuda.synchronize()
+    assert intact(big_a, n_panel) and intact(big_c, n_panel) and intact(big_y, m * 2) and intact(big_r, m * f)
+    h1 = torch.relu(x2.double() @ w_in.double().t() + b_in.double())
+    assert rel(rows.view(m, f), h1 @ w.double().t()) < 1e-5          # the last launch was the plain product
+    assert rel(y.view(m, 2), (h1 @ w.double().t()) @ w_out.double().t()) < 1e-5
+    big_p, pp = guarded(n_panel)
+    native._check(lib.sb_mlp_pack_rows(rows.data_ptr(), m, f, pp.data_ptr(), s), "pack_rows")
+    torch.cuda.synchronize()
+    assert intact(big_p, n_panel)

@@ -1,5 +1,6 @@
+"""Both fp32 RK4 rollout kernels (two / one initial condition per thread) at the shard sizes of a 1e6-IC rollout over 8, 4, 2, 1 GPUs."""
 import os, sys, torch
-ROOT = "/root/repo"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "symmetry-ode-discovery_b200")]
 from sindy_b200 import native
 def timeit(fn, reps=5):
