@@ -751,7 +751,8 @@ int launch_fused(const FusedArgs& a, void* ws, int64_t ws_bytes, cudaStream_t s,
   // sample ahead pays where the loop is short enough to be latency-bound (K = 10) and costs registers / issue slots
   // where the FMA pipe is the limit (K = 20). Two samples per thread and iteration (two independent chains) was also
   // tried on the 2048x3 ring: (2,3) 0.327, (3,3) 0.686 — slower (170 registers, the second expansion competes for the
-  // same FMA pipe); removed.
+  // same FMA pipe); removed. A 2048 x 2 ring (room for a second resident CTA at d = 3: 16 warps per SM instead of 8) is
+  // a wash: (3,3) 0.556 against 0.560, (2,3) 0.322 against 0.290 — occupancy is not what limits these shapes; removed.
   const int chosen = small_variant() ? small_variant() : ((D == 2 && P == 3) ? 45 : 13);
   switch (chosen) {
     case 13: return launch_fused_var<D, P, LEFT, 13>(a, ws, ws_bytes, s, slot);   // 2048 x 3 ring
