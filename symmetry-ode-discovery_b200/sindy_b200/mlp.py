@@ -247,6 +247,8 @@ class FrozenMLP:
 
     def value(self, x: torch.Tensor) -> torch.Tensor:
         rows = self._rows(x, "x")
+        if rows.shape[0] == 0:
+            return self._shape_out(rows.new_zeros(0, self.out_dim), x)
         if torch.is_grad_enabled() and x.requires_grad:
             y = _Value.apply(rows, self)
         else:
@@ -260,6 +262,9 @@ class FrozenMLP:
         rows, trows = self._rows(x, "x"), self._rows(t, "t")
         if trows.shape[0] != rows.shape[0]:
             raise ValueError("x and t must describe the same rows")
+        if rows.shape[0] == 0:
+            z = rows.new_zeros(0, self.out_dim)
+            return self._shape_out(z, x), self._shape_out(z.clone(), x)
         if torch.is_grad_enabled() and (x.requires_grad or t.requires_grad):
             y, jt = _ValueJvp.apply(rows, trows, self)
         else:

@@ -288,3 +288,39 @@ def test_layer_kernels_write_inside_their_buffers(mlp, variant, monkeypatch):
     native._check(lib.sb_mlp_pack_rows(rows.data_ptr(), m, f, pp.data_ptr(), s), "pack_rows")
     torch.cuda.synchronize()
     assert intact(big_p, n_panel)
+
+
+@pytest.mark.parametrize("in_dim,hidden,out_dim,n_layers", [(1, 256, 1, 2), (3, 256, 5, 3), (8, 1024, 8, 3), (2, 512, 2, 1)])
+def test_other_network_shapes_and_input_forms(mlp, in_dim, hidden, out_dim, n_layers):
+    """Thin dimensions 1..8, hidden widths 256 / 512 / 1024, one to three hidden layers (n_layers = 1: no wide layer at
+    all, only the two thin kernels); empty batches, non-contiguous and float64 inputs, no leading batch structure."""
+    torch.manual_seed(in_dim + hidden)
+    mods = [nn.Linear(in_dim, hidden), nn.ReLU()]
+    for _ in range(n_layers - 1):
+        mods += [nn.Linear(hidden, hidden), nn.ReLU()]
+    mods += [nn.Linear(hidden, out_dim)]
+    net = nn.Sequential(*mods).cuda().eval()
+    for p in net.parameters():
+        p.requires_grad_(False)
+    fast = mlp.FrozenMLP.from_module(net)
+    assert fast is not None
+    net64 = nn.Sequential(*mods).double()
+    x = torch.randn(333, in_dim, device="cuda")
+    t = torch.randn(333, in_dim, device="cuda")
+    assert rel(fast.value(x), net64(x.double())) < 2e-5
+    _, jt64 = torch.autograd.functional.jvp(net64, x.double(), t.double())
+    assert rel_rows(fast.value_and_jvp(x, t)[1], jt64) < 2e-5
+    # empty batch, 1-D sample, non-contiguous view, float64 input
+    assert fast.value(x[:0]).shape == (0, out_dim) and fast.value_and_jvp(x[:0], t[:0])[1].shape == (0, out_dim)
+    assert fast.value(x[5]).shape == (out_dim,) and rel(fast.value(x[5]), net64(x[5].double())) < 2e-5
+    wide = torch.randn(333, 2 * in_dim, device="cuda")
+    assert rel(fast.value(wide[:, ::2]), net64(wide[:, ::2].double())) < 2e-5
+    assert rel(fast.value(x.double()), net64(x.double())) < 2e-5
+    xg = x.clone().requires_grad_(True)
+    c = torch.randn(333, out_dim, device="cuda")
+    (fast.value(xg) * c).sum().backward()
+    x64 = x.double().requires_grad_(True)
+    (net64(x64) * c.double()).sum().backward()
+    assert rel_rows(xg.grad, x64.grad) < 2e-5
+    with pytest.raises(ValueError):
+        fast.value(torch.randn(4, in_dim + 1, device="cuda"))
