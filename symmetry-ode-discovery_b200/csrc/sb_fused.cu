@@ -894,10 +894,120 @@ __global__ void __launch_bounds__(256) forward_spec_kernel(const float* __restri
   }
 }
 
+// The same forward with x staged through shared memory by 1-D bulk copies (the fused kernel's ring): ncu showed the
+// grid-stride kernel waiting on its own global loads (long scoreboard 4.97 per issue, FMA pipe 73.6 % active) even with
+// the next sample requested one iteration ahead. Persistent CTAs, tiles dealt round-robin, y written straight from
+// registers (a warp's 32 samples are 32·d contiguous floats).
+constexpr int kFwdTile = 2048, kFwdStages = 3, kFwdThreads = 256;
+
+template <int D, int P>
+__global__ void __launch_bounds__(kFwdThreads, 2) forward_tma_kernel(const float* __restrict__ x, int64_t n,
+                                                                     float* __restrict__ y) {
+  using C = Cfg<D, P, 1>;
+  extern __shared__ __align__(128) unsigned char fwd_smem[];
+  float* tiles = reinterpret_cast<float*>(fwd_smem);
+  uint64_t* full = reinterpret_cast<uint64_t*>(fwd_smem + (size_t)kFwdStages * kFwdTile * D * sizeof(float));
+  uint64_t* empty = full + kFwdStages;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int64_t n_bulk = n & ~(int64_t)3;                       // bulk copies move multiples of 16 bytes
+  const int64_t n_tiles = (n_bulk + kFwdTile - 1) / kFwdTile;
+  const int my_tiles = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);   // tiles b, b + grid, ...
+  auto tile_first = [&](int it) { return ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kFwdTile; };
+  auto tile_count = [&](int it) {
+    const int64_t left = n_bulk - tile_first(it);
+    return (int)(left < kFwdTile ? left : kFwdTile);
+  };
+  auto issue = [&](int it, int stage) {
+    const uint32_t bytes = (uint32_t)tile_count(it) * D * sizeof(float);
+    mbar_expect_tx(&full[stage], bytes);
+    tma_load_1d(tiles + (size_t)stage * kFwdTile * D, x + tile_first(it) * D, bytes, &full[stage]);
+  };
+  if (tid == 0) {
+    for (int s = 0; s < kFwdStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kFwdThreads / 32); }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid == 0)
+    for (int s = 0; s < kFwdStages && s < my_tiles; ++s) issue(s, s);
+
+  auto one_sample = [&](const float (&xs)[D], int64_t smp) {
+    float m[C::K];
+    expand_lib<D, P>(xs, m);
+    float2 pred[D][2];
+    static_for<0, D>([&](auto i) { pred[i][0] = make_float2(0.f, 0.f); pred[i][1] = make_float2(0.f, 0.f); });
+    static_for<0, C::K2>([&](auto kc) {
+      constexpr int kk = kc;
+      const float2 m2 = make_float2(m[2 * kk], (2 * kk + 1 < C::K) ? m[2 * kk + 1] : 0.f);
+      static_for<0, D>([&](auto ic) {
+        constexpr int i = ic;
+        pred[i][kk % 2] = __ffma2_rn(c_w2[i * C::K2 + kk], m2, pred[i][kk % 2]);
+      });
+    });
+    static_for<0, D>([&](auto i) {
+      y[smp * D + i] = (pred[i][0].x + pred[i][0].y) + (pred[i][1].x + pred[i][1].y);
+    });
+  };
+
+  for (int it = 0; it < my_tiles; ++it) {
+    const int stage = it % kFwdStages;
+    if (tid == 0 && it >= 1) {                                   // refill the stage consumed one tile ago
+      const int next = it + kFwdStages - 1;
+      if (next < my_tiles) {
+        const int ps = (it - 1) % kFwdStages;
+        mbar_wait(&empty[ps], (uint32_t)((it - 1) / kFwdStages) & 1u);
+        issue(next, ps);
+      }
+    }
+    mbar_wait(&full[stage], (uint32_t)(it / kFwdStages) & 1u);
+    const float* sx = tiles + (size_t)stage * kFwdTile * D;
+    const int cnt = tile_count(it);
+    const int64_t first = tile_first(it);
+#pragma unroll 1
+    for (int j = tid; j < cnt; j += kFwdThreads) {
+      float xs[D];
+      static_for<0, D>([&](auto q) { xs[q] = sx[j * D + q]; });
+      one_sample(xs, first + j);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[stage]);
+  }
+  if (blockIdx.x == 0) {                                         // the n mod 4 samples no bulk copy covers
+    const int64_t j = n_bulk + tid;
+    if (j < n) {
+      float xs[D];
+      static_for<0, D>([&](auto q) { xs[q] = __ldg(x + j * D + q); });
+      one_sample(xs, j);
+    }
+  }
+}
+
 template <int D, int P>
 int run_forward(const float* x, int64_t n, const float* w, float* y, cudaStream_t s) {
   int st = upload_w<D, P>(w, nullptr, 0, s);
   if (st != SB_OK) return st;
+  const char* e_ring = getenv("SB_FORWARD_RING");               // A/B switch, read per call
+  const bool no_ring = e_ring && e_ring[0] == '0';
+  if (n >= (int64_t)148 * 2 * kFwdTile && !no_ring && (reinterpret_cast<uintptr_t>(x) & 15u) == 0) {
+    constexpr size_t smem = (size_t)kFwdStages * kFwdTile * D * sizeof(float) + 2 * kFwdStages * sizeof(uint64_t);
+    auto kern = forward_tma_kernel<D, P>;
+    static int grid_cached[64] = {0};
+    int dev = 0;
+    SB_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) { set_error("device index %d out of range", dev); return SB_ERR_INVALID; }
+    {
+      std::lock_guard<std::mutex> lock(g_init_mutex);
+      if (grid_cached[dev] == 0) {
+        SB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0, sms = 0;
+        SB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kFwdThreads, smem));
+        SB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        grid_cached[dev] = (per_sm < 1 ? 1 : per_sm) * sms;
+      }
+    }
+    kern<<<grid_cached[dev], kFwdThreads, smem, s>>>(x, n, y);
+    SB_LAUNCH_CHECK("forward_tma_kernel");
+    return SB_OK;
+  }
   int64_t blocks = (n + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   forward_spec_kernel<D, P><<<(unsigned)blocks, 256, 0, s>>>(x, n, y);

@@ -734,3 +734,23 @@ def test_golden_gp_smoother(golden):
         assert X.dtype == np.float64 and X.shape == g[name + "_X"].shape
         assert rel(X, g[name + "_X"]) < 1e-9, rel(X, g[name + "_X"])
         assert rel(dX, g[name + "_dX"]) < 1e-6, rel(dX, g[name + "_dX"])
+
+
+@pytest.mark.parametrize("d,p,e", [(3, 5, 0), (3, 3, 0), (2, 3, 0), (2, 2, 1), (2, 2, 0)])
+def test_forward_through_the_bulk_copy_ring_is_bitwise_the_grid_stride_kernel(nat, d, p, e, monkeypatch):
+    """Large batches run h(x) = Θ(x)Wᵀ through `forward_tma_kernel` (x staged by 1-D bulk copies); per sample the
+    arithmetic is that of `forward_spec_kernel`: identical bits, ragged sizes (n mod 4 != 0, last tile partial) too,
+    and both agree with the oracle on a sample."""
+    lib = nat.Library(d, p, False, bool(e))
+    gen = torch.Generator(device="cuda").manual_seed(31 * d + p)
+    W = 0.3 * torch.randn(d, lib.K, device="cuda", generator=gen)
+    for n in (148 * 2 * 2048, 700001, 1000003):
+        x = torch.rand(n, d, device="cuda", generator=gen) * 1.6 - 0.8
+        monkeypatch.setenv("SB_FORWARD_RING", "1")
+        ya = nat.forward(x, W, lib)
+        monkeypatch.setenv("SB_FORWARD_RING", "0")
+        yb = nat.forward(x, W, lib)
+        assert torch.equal(ya, yb), (d, p, e, n)
+    idx = torch.randint(0, n, (2000,), device="cuda", generator=gen)
+    want = O.theta(x[idx].cpu().numpy().astype(np.float64), p, False, bool(e)) @ W.double().cpu().numpy().T
+    assert rel(ya[idx], want) < 2e-6
