@@ -78,6 +78,8 @@ def _fast_ae(autoencoder, x):
     mode = os.environ.get("SINDY_B200_AE_MLP", "1")
     if not (torch.is_tensor(x) and x.is_cuda) or mode == "0":
         return None
+    if torch._C._functorch.maybe_current_level() is not None:
+        return None       # inside vmap / jacfwd (`precompute_symmreg_r`, `model_utils.py:172-211`): PyTorch modules only
     pair = _mlp.accelerate(autoencoder)
     if pair is None and mode == "require":          # tests: prove that the tensor-core path is the one that ran
         raise RuntimeError("SINDY_B200_AE_MLP=require: this autoencoder is not served by sindy_b200.mlp.FrozenMLP")

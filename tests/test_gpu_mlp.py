@@ -225,6 +225,10 @@ def test_symmetry_regularisers_through_the_tensor_core_chain(mlp, monkeypatch):
         out["r"] = (float(lr), reg.Xi.grad.clone())
         gx, jgx = model_utils.group_action_and_jacobian(x, ae, gen)
         out["g"] = (torch.stack(gx), torch.stack(jgx))
+        # the reference's own precompute (vmap(jacfwd(...)), `model_utils.py:172-211`) runs under functorch transforms:
+        # the tensor-core chain steps aside there and the result is the PyTorch one whatever the switch says
+        gx_p, jgx_p = model_utils.precompute_symmreg_r(x[:64], ae, gen)
+        out["p"] = (torch.stack(gx_p), torch.stack(jgx_p))
         return out
 
     fast = run()
@@ -234,6 +238,7 @@ def test_symmetry_regularisers_through_the_tensor_core_chain(mlp, monkeypatch):
     for k in "ifr":
         assert abs(fast[k][0] - slow[k][0]) < 1e-4 * abs(slow[k][0]), k
         assert rel(fast[k][1], slow[k][1]) < 5e-4, k
+    assert rel(fast["p"][0], slow["p"][0]) < 1e-5 and rel(fast["p"][1], slow["p"][1]) < 1e-6
     assert rel(fast["g"][0][0], slow["g"][0][0]) < 1e-5 and rel_rows(fast["g"][1][0], slow["g"][1][0]) < 1e-4
 
 
