@@ -86,13 +86,13 @@ def _fast_ae(autoencoder, x):
     return pair
 
 
-def _encode(autoencoder, x):
-    fast = _fast_ae(autoencoder, x)
+def _encode(autoencoder, x, fast_ok=True):
+    fast = _fast_ae(autoencoder, x) if fast_ok else None
     return fast[0].value(x) if fast is not None else autoencoder.encode(x)
 
 
-def _decode(autoencoder, z):
-    fast = _fast_ae(autoencoder, z)
+def _decode(autoencoder, z, fast_ok=True):
+    fast = _fast_ae(autoencoder, z) if fast_ok else None
     return fast[1].value(z) if fast is not None else autoencoder.decode(z)
 
 
@@ -104,9 +104,9 @@ def _decoder_tangent(autoencoder, z, v, require_grad):
     return _jvp_fn(require_grad)(autoencoder.decoder, z, v=v)[1]
 
 
-def _centred_latent(autoencoder, x, normalize, z_mean):
+def _centred_latent(autoencoder, x, normalize, z_mean, fast_ok=True):
     """z = encode(x) − centre, centre = batch mean ('in_batch') or z_mean / last BatchNorm bias ('global')."""
-    z = _encode(autoencoder, x)
+    z = _encode(autoencoder, x, fast_ok)
     if normalize == 'in_batch':
         z = z - z.mean(dim=0, keepdim=True)
     elif normalize == 'global':
@@ -194,10 +194,10 @@ def symmreg_f(x_fx, autoencoder, generator, f, normalize='global', z_mean=None, 
     return loss.cpu().numpy() if numpy else loss
 
 
-def _group_transform(autoencoder, g, x, normalize='global', z_mean=None):
+def _group_transform(autoencoder, g, x, normalize='global', z_mean=None, fast_ok=True):
     """x -> decode(g·(encode(x) − centre) + centre), first component (reference `model_utils.py:145-158`)."""
-    z, z_mean = _centred_latent(autoencoder, torch.stack([x, x], dim=1), normalize, z_mean)
-    return _decode(autoencoder, _act_on_latent(g, z) + z_mean)[:, 0]
+    z, z_mean = _centred_latent(autoencoder, torch.stack([x, x], dim=1), normalize, z_mean, fast_ok)
+    return _decode(autoencoder, _act_on_latent(g, z) + z_mean, fast_ok)[:, 0]
 
 
 def _group_transform_jvp(autoencoder, g, x, v, normalize, z_mean, require_grad):
@@ -205,7 +205,9 @@ def _group_transform_jvp(autoencoder, g, x, v, normalize, z_mean, require_grad):
     tangent is pushed through encoder, latent action and decoder in forward mode; otherwise the reference's double vjp."""
     fast = _fast_ae(autoencoder, x)
     if fast is None or normalize != 'global':         # 'in_batch': the batch mean couples the rows, keep autograd's graph
-        move = partial(_group_transform, autoencoder, g, normalize=normalize, z_mean=z_mean)
+        # the double vjp differentiates its function twice: PyTorch modules only (the tensor-core operators are
+        # first-order)
+        move = partial(_group_transform, autoencoder, g, normalize=normalize, z_mean=z_mean, fast_ok=False)
         return move(x), _jvp_fn(require_grad)(move, x, v=v)[1]
     enc, dec = fast
     z, dz = enc.value_and_jvp(torch.stack([x, x], dim=1), torch.stack([v, v], dim=1))

@@ -223,6 +223,10 @@ def test_symmetry_regularisers_through_the_tensor_core_chain(mlp, monkeypatch):
         lr = model_utils.symmreg_r(x, ae, gen, h=reg, require_grad=True)
         reg.zero_grad(); lr.backward()
         out["r"] = (float(lr), reg.Xi.grad.clone())
+        lb = model_utils.symmreg_r(x[:512], ae, gen, h=reg, normalize='in_batch', z_mean=ae.encoder[-2].bias,
+                                    require_grad=True)                  # double-vjp branch (PyTorch modules)
+        reg.zero_grad(); lb.backward()
+        out["b"] = (float(lb), reg.Xi.grad.clone())
         gx, jgx = model_utils.group_action_and_jacobian(x, ae, gen)
         out["g"] = (torch.stack(gx), torch.stack(jgx))
         # the reference's own precompute (vmap(jacfwd(...)), `model_utils.py:172-211`) runs under functorch transforms:
@@ -235,7 +239,7 @@ def test_symmetry_regularisers_through_the_tensor_core_chain(mlp, monkeypatch):
     assert ae.__dict__.get("_sb_frozen_mlps", (None, None))[1] is not None
     monkeypatch.setenv("SINDY_B200_AE_MLP", "0")
     slow = run()
-    for k in "ifr":
+    for k in "ifrb":
         assert abs(fast[k][0] - slow[k][0]) < 1e-4 * abs(slow[k][0]), k
         assert rel(fast[k][1], slow[k][1]) < 5e-4, k
     assert rel(fast["p"][0], slow["p"][0]) < 1e-5 and rel(fast["p"][1], slow["p"][1]) < 1e-6
