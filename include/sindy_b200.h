@@ -277,7 +277,8 @@ int sb_wsindy_integrals(const float* x, int64_t n_traj, int64_t T, const sb_libr
  * the tensor core consumes: sb_mlp_panel_bytes(m, f) bytes for an (m × f) tensor (rows padded to 128; per 128-row tile and
  * 16-feature block a contiguous 16 KB [tf32-hi | lo] pair in the canonical K-major core-matrix layout), so that a
  * layer's epilogue writes the next layer's operand and the operand ring is filled by plain bulk copies.
- *  - sb_mlp_pack_weights: B[n][k] = w[n·k_dim + k] (transpose = 0) or w[k·n + n_idx] (transpose = 1) → packed, 8·n·k bytes.
+ *  - sb_mlp_pack_weights: B (n × k) from w: transpose = 0: w is B row-major (B[i][j] = w[i·k + j]); transpose = 1: w is Bᵀ
+ *    row-major (B[i][j] = w[j·n + i]). packed: 8·n·k bytes. n a multiple of 256, k a multiple of 256 (≤ 2048).
  *  - sb_mlp_pack_rows / sb_mlp_unpack_rows: (m × f) row-major fp32 ↔ panel format (tests, wide inputs).
  *  - sb_mlp_thin_in: C = epilogue(x · wᵀ [+ bias]), x (m × in_dim ≤ 8) row-major, w (f × in_dim), panel-format output.
  *  - sb_mlp_thin_out: y (m × out_dim ≤ 8, row-major) = A · wᵀ [+ bias], A in panel format, w (out_dim × f).

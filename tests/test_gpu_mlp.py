@@ -333,3 +333,25 @@ def test_other_network_shapes_and_input_forms(mlp, in_dim, hidden, out_dim, n_la
     assert rel_rows(xg.grad, x64.grad) < 2e-5
     with pytest.raises(ValueError):
         fast.value(torch.randn(4, in_dim + 1, device="cuda"))
+
+
+@pytest.mark.parametrize("k,n", [(256, 512), (512, 256), (1024, 256), (256, 1024)])
+def test_wide_layer_kernel_rectangular(mlp, k, n):
+    """sb_mlp_gemm with different input and output widths (C (m × n) = A (m × k)·Bᵀ, B (n × k)), both weight packings."""
+    from sindy_b200 import native
+    lib = native.load()
+    g = torch.Generator(device="cuda").manual_seed(k + n)
+    m = 777
+    a = torch.randn(m, k, device="cuda", generator=g)
+    w = torch.randn(n, k, device="cuda", generator=g) / k ** 0.5
+    b = torch.randn(n, device="cuda", generator=g)
+    s = native._stream(a.device)
+    pa, pc = mlp._Panel.from_rows(a), mlp._Panel(m, n, a.device)
+    pk = torch.empty(2 * n * k, device="cuda")
+    native._check(lib.sb_mlp_pack_weights(w.data_ptr(), n, k, 0, pk.data_ptr(), s), "pack")
+    native._check(lib.sb_mlp_gemm(pa.ptr(), m, k, pk.data_ptr(), n, b.data_ptr(), None, 1, pc.ptr(), s), "gemm")
+    assert rel(pc.to_rows(), torch.relu(a.double() @ w.double().t() + b.double())) < 1e-5
+    wt = w.t().contiguous()                                   # (k × n): the same B from its transpose
+    native._check(lib.sb_mlp_pack_weights(wt.data_ptr(), n, k, 1, pk.data_ptr(), s), "pack")
+    native._check(lib.sb_mlp_gemm(pa.ptr(), m, k, pk.data_ptr(), n, None, None, 0, pc.ptr(), s), "gemm")
+    assert rel(pc.to_rows(), a.double() @ w.double().t()) < 1e-5
