@@ -283,6 +283,11 @@ int sb_wsindy_integrals(const float* x, int64_t n_traj, int64_t T, const sb_libr
  *  - sb_mlp_thin_in: C = epilogue(x · wᵀ [+ bias]), x (m × in_dim ≤ 8) row-major, w (f × in_dim), panel-format output.
  *  - sb_mlp_thin_out: y (m × out_dim ≤ 8, row-major) = A · wᵀ [+ bias], A in panel format, w (out_dim × f).
  *  - sb_mlp_gemm: the wide layer above; bias (n floats) and mask_panel may be NULL as the mode allows.
+ *  - sb_mlp_gemm_out: the wide layer with the thin OUTPUT layer fused into its epilogue: y (m × out_dim) = C · w_outᵀ
+ *    [+ bias_out], w_out (out_dim × n) row-major; c_panel may be NULL when the wide activations are not needed
+ *    afterwards (tangent and cotangent chains). partials: scratch of sb_mlp_partials_bytes(m, n, out_dim) bytes — per
+ *    64-column granule the row's partial products, added in granule order by a second tiny launch, so y does not
+ *    depend on how tiles were scheduled.
  * All pointers to panel / packed buffers must be 16-byte aligned. */
 int64_t sb_mlp_panel_bytes(int64_t m, int f);
 int sb_mlp_pack_weights(const float* w, int n, int k, int transpose, void* packed, void* stream);
@@ -294,6 +299,10 @@ int sb_mlp_thin_out(const void* a_panel, int64_t m, int f, const float* w, const
                     void* stream);
 int sb_mlp_gemm(const void* a_panel, int64_t m, int k, const void* w_packed, int n, const float* bias,
                 const void* mask_panel, int mode, void* c_panel, void* stream);
+int64_t sb_mlp_partials_bytes(int64_t m, int n, int out_dim);
+int sb_mlp_gemm_out(const void* a_panel, int64_t m, int k, const void* w_packed, int n, const float* bias,
+                    const void* mask_panel, int mode, void* c_panel, const float* w_out, const float* bias_out,
+                    int out_dim, void* partials, float* y, void* stream);
 
 /* Debug/profiling aid: while dev_buf (device memory, 16 uint64 per CTA, at least 16·592 words) is set, every fused
  * kernel launched afterwards records %globaltimer stamps of its phases per CTA: 0 entry, 1 first tile landed, 2 end of

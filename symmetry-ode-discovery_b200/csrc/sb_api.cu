@@ -474,6 +474,23 @@ int sb_mlp_gemm(const void* a_panel, int64_t m, int k, const void* w_packed, int
   return mlp_gemm(a_panel, m, k, w_packed, n, bias, mask_panel, mode, c_panel, (cudaStream_t)stream);
 }
 
+int64_t sb_mlp_partials_bytes(int64_t m, int n, int out_dim) {
+  return (m < 0 || n <= 0 || out_dim <= 0) ? 0 : mlp_partials_bytes(m, n, out_dim);
+}
+
+int sb_mlp_gemm_out(const void* a_panel, int64_t m, int k, const void* w_packed, int n, const float* bias,
+                    const void* mask_panel, int mode, void* c_panel, const float* w_out, const float* bias_out,
+                    int out_dim, void* partials, float* y, void* stream) {
+  if (m < 0) { set_error("bad size m=%lld", (long long)m); return SB_ERR_INVALID; }
+  SB_TRY(check_16(a_panel, "a_panel")); SB_TRY(check_16(w_packed, "w_packed")); SB_TRY(check_16(w_out, "w_out"));
+  if (c_panel) SB_TRY(check_16(c_panel, "c_panel"));
+  if (bias) SB_TRY(check_16(bias, "bias"));
+  if (mask_panel) SB_TRY(check_16(mask_panel, "mask_panel"));
+  if (m > 0) { SB_TRY(check_ptr(partials, "partials")); SB_TRY(check_ptr(y, "y")); }
+  return mlp_gemm_out(a_panel, m, k, w_packed, n, bias, mask_panel, mode, c_panel, w_out, bias_out, out_dim, partials, y,
+                      (cudaStream_t)stream);
+}
+
 int sb_mlp_thin_in(const float* x, int64_t m, int in_dim, const float* w, const float* bias, const void* mask_panel,
                    int f, int mode, void* c_panel, void* stream) {
   if (m < 0) { set_error("bad size m=%lld", (long long)m); return SB_ERR_INVALID; }

@@ -317,6 +317,10 @@ int mlp_pack_rows(const float* x, int64_t m, int f, void* packed, cudaStream_t s
 int mlp_unpack_rows(const void* packed, int64_t m, int f, float* x, cudaStream_t s);
 int mlp_gemm(const void* a_panel, int64_t m, int k, const void* w_packed, int n, const float* bias,
              const void* mask_panel, int mode, void* c_panel, cudaStream_t s);
+int64_t mlp_partials_bytes(int64_t m, int n, int out_dim);
+int mlp_gemm_out(const void* a_panel, int64_t m, int k, const void* w_packed, int n, const float* bias,
+                 const void* mask_panel, int mode, void* c_panel, const float* w_out, const float* bias_out,
+                 int out_dim, void* partials, float* y, cudaStream_t s);
 int mlp_thin_in(const float* x, int64_t m, int in_dim, const float* w, const float* bias, const void* mask_panel,
                 int f, int mode, void* c_panel, cudaStream_t s);
 int mlp_thin_out(const void* a_panel, int64_t m, int f, const float* w, const float* bias, int out_dim, float* y,

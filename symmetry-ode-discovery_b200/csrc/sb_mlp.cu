@@ -43,6 +43,7 @@ constexpr uint32_t kTmemCols = 512;
 constexpr size_t kSmem = 1024 + (size_t)kStages * kStageBytes + 256;
 
 enum : int { kLin = 0, kRelu = 1, kMask = 2 };
+constexpr int kThinMax = 8;                                    // widest thin (first / last) layer
 
 struct GemmArgs {
   const unsigned char* A;   // panel format, m_tiles × k_blocks blocks
@@ -51,6 +52,10 @@ struct GemmArgs {
   const unsigned char* R;   // panel format like C: mask source (kMask)
   unsigned char* C;         // panel format, m_tiles × (n_tiles·16) blocks
   int m_tiles, k_blocks, n_tiles, mode;
+  const float* w_out;       // fused thin output layer (one-CTA kernel): (out_dim × n) row-major, or null
+  float* partials;          // [n/64][m_pad][out_dim]: per 64-column granule the partial products of every row
+  int out_dim;
+  int64_t m_pad;
   int full_tiles, split, items;   // one-CTA kernel: work items = full 128×256 tiles, then the last partial round as
                                   // `split` narrower pieces per tile (128 × 256/split) so that it fills the SMs
 };
@@ -227,6 +232,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_gemm_kernel(GemmArgs a) {
       const unsigned char* Rp = a.R ? a.R + panel : nullptr;
       const float* bias = a.bias ? a.bias + pc.nt * kBN + pc.n0 : nullptr;
       const int col_hi = col_lo + kBN / (kEpiWarps / 4) < pc.bn ? col_lo + kBN / (kEpiWarps / 4) : pc.bn;
+      float oacc[kThinMax];
+#pragma unroll
+      for (int o = 0; o < kThinMax; ++o) oacc[o] = 0.f;
 #pragma unroll 1
       for (int c0 = col_lo; c0 < col_hi; c0 += 16) {
         uint32_t r[16];
@@ -260,9 +268,39 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_gemm_kernel(GemmArgs a) {
             v[4 * e4 + 3] = m4.w > 0.f ? v[4 * e4 + 3] : 0.f;
           }
         }
+        if (a.C) {
 #pragma unroll
-        for (int e4 = 0; e4 < 4; ++e4)
-          store_split(Cp + blk, kABlock, row_off + e4 * kLBO, v[4 * e4], v[4 * e4 + 1], v[4 * e4 + 2], v[4 * e4 + 3]);
+          for (int e4 = 0; e4 < 4; ++e4)
+            store_split(Cp + blk, kABlock, row_off + e4 * kLBO, v[4 * e4], v[4 * e4 + 1], v[4 * e4 + 2], v[4 * e4 + 3]);
+        }
+        if (a.w_out) {
+          // fused thin output layer: per 64-column granule the row's partial products with the (out_dim × n) matrix;
+          // `mlp_sum_partials_kernel` adds the granules in index order — the association is fixed by the column
+          // partition alone, whatever tile or piece computed a granule
+          const int ncol = pc.nt * kBN + pc.n0 + c0;
+          const int n_all = a.n_tiles * kBN;
+          auto dot = [&](int o) {
+            const float4* wp = reinterpret_cast<const float4*>(a.w_out + (size_t)o * n_all + ncol);
+            float sacc = oacc[o];
+#pragma unroll
+            for (int e4 = 0; e4 < 4; ++e4) {
+              const float4 w4 = __ldg(wp + e4);
+              sacc = fmaf(v[4 * e4], w4.x, sacc); sacc = fmaf(v[4 * e4 + 1], w4.y, sacc);
+              sacc = fmaf(v[4 * e4 + 2], w4.z, sacc); sacc = fmaf(v[4 * e4 + 3], w4.w, sacc);
+            }
+            oacc[o] = sacc;
+          };
+          dot(0);
+          if (a.out_dim > 1) dot(1);
+          if (a.out_dim > 2) { dot(2); if (a.out_dim > 3) dot(3); }
+          if (a.out_dim > 4) { dot(4); if (a.out_dim > 5) dot(5); if (a.out_dim > 6) dot(6); if (a.out_dim > 7) dot(7); }
+          if (((c0 + 16) & 63) == 0) {
+            float* dst = a.partials + ((size_t)((ncol + 16) / 64 - 1) * a.m_pad + (size_t)pc.mt * kBM + row) * a.out_dim;
+#pragma unroll
+            for (int o = 0; o < kThinMax; ++o)
+              if (o < a.out_dim) { dst[o] = oacc[o]; oacc[o] = 0.f; }
+          }
+        }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -494,7 +532,6 @@ struct InArgs {
   const float* w; const float* bias; const unsigned char* R; unsigned char* C;
   int F, mode;
 };
-constexpr int kThinMax = 8;
 
 __global__ void __launch_bounds__(128) mlp_in_kernel(InArgs a) {
   __shared__ float ws[128 * kThinMax];
@@ -632,6 +669,18 @@ __global__ void mlp_unpack_rows_kernel(const unsigned char* P, int64_t m, int F,
   *reinterpret_cast<float4*>(x + r * F + k) = make_float4(hi.x + lo.x, hi.y + lo.y, hi.z + lo.z, hi.w + lo.w);
 }
 
+// y[m][o] = (bias[o]) + Σ_g partials[g][m][o], granules in index order
+__global__ void mlp_sum_partials_kernel(const float* partials, int64_t m, int64_t m_pad, int n_granules, int out_dim,
+                                        const float* bias, float* y) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= m * out_dim) return;
+  const int64_t row = idx / out_dim;
+  const int o = (int)(idx % out_dim);
+  float s = bias ? bias[o] : 0.f;
+  for (int g = 0; g < n_granules; ++g) s += partials[((size_t)g * m_pad + row) * out_dim + o];
+  y[idx] = s;
+}
+
 int check_wide(int f, const char* what) {
   if (f <= 0 || f % kBN != 0 || f > 2048) {
     set_error("sb_mlp: %s = %d must be a positive multiple of %d (<= 2048)", what, f, kBN);
@@ -678,9 +727,25 @@ int mlp_unpack_rows(const void* packed, int64_t m, int f, float* x, cudaStream_t
   return SB_OK;
 }
 
+int64_t mlp_partials_bytes(int64_t m, int n, int out_dim) {
+  return (int64_t)(n / 64) * ((m + 127) / 128 * 128) * out_dim * (int64_t)sizeof(float);
+}
+
 int mlp_gemm(const void* a_panel, int64_t m, int k, const void* w_packed, int n, const float* bias,
              const void* mask_panel, int mode, void* c_panel, cudaStream_t s) {
+  return mlp_gemm_out(a_panel, m, k, w_packed, n, bias, mask_panel, mode, c_panel, nullptr, nullptr, 0, nullptr, nullptr, s);
+}
+
+int mlp_gemm_out(const void* a_panel, int64_t m, int k, const void* w_packed, int n, const float* bias,
+                 const void* mask_panel, int mode, void* c_panel, const float* w_out, const float* bias_out,
+                 int out_dim, void* partials, float* y, cudaStream_t s) {
   SB_TRY(check_wide(n, "n")); SB_TRY(check_wide(k, "k"));
+  if (w_out) {
+    SB_TRY(check_thin(out_dim, "out_dim"));
+    if (!partials || !y) { set_error("sb_mlp_gemm_out: partials / y missing"); return SB_ERR_INVALID; }
+  } else if (!c_panel) {
+    set_error("sb_mlp_gemm: no output requested"); return SB_ERR_INVALID;
+  }
   if (mode < kLin || mode > kMask) { set_error("sb_mlp_gemm: mode %d", mode); return SB_ERR_INVALID; }
   if (mode == kMask && !mask_panel) { set_error("sb_mlp_gemm: mask mode without a mask panel"); return SB_ERR_INVALID; }
   if (m <= 0) return SB_OK;
@@ -707,7 +772,8 @@ int mlp_gemm(const void* a_panel, int64_t m, int k, const void* w_packed, int n,
   a.A = (const unsigned char*)a_panel; a.W = (const unsigned char*)w_packed; a.bias = bias;
   a.R = (const unsigned char*)mask_panel; a.C = (unsigned char*)c_panel;
   a.m_tiles = (int)((m + 127) / 128); a.k_blocks = k / kBK; a.n_tiles = n / kBN; a.mode = mode;
-  if (pairs) {
+  a.w_out = w_out; a.partials = (float*)partials; a.out_dim = out_dim; a.m_pad = (int64_t)a.m_tiles * kBM;
+  if (pairs && !w_out) {
     const int tiles2 = ((a.m_tiles + 1) / 2) * a.n_tiles;
     const int max_pairs = sm_count[dev] / 2;
     const int grid2 = 2 * (tiles2 < max_pairs ? tiles2 : max_pairs);
@@ -727,6 +793,12 @@ int mlp_gemm(const void* a_panel, int64_t m, int k, const void* w_packed, int n,
   if (split) mlp_gemm_kernel<true><<<grid, kThreads, kSmem, s>>>(a);
   else mlp_gemm_kernel<false><<<grid, kThreads, kSmem, s>>>(a);
   SB_LAUNCH_CHECK("mlp_gemm_kernel");
+  if (w_out) {
+    const int64_t units = m * out_dim;
+    mlp_sum_partials_kernel<<<(unsigned)((units + 255) / 256), 256, 0, s>>>((const float*)partials, m, a.m_pad, n / 64,
+                                                                          out_dim, bias_out, y);
+    SB_LAUNCH_CHECK("mlp_sum_partials_kernel");
+  }
   return SB_OK;
 }
 

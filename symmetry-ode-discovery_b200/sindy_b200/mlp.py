@@ -177,62 +177,69 @@ class FrozenMLP:
             return None
 
     # ---- chains (rows: (m × in_dim) fp32 contiguous) ----
-    def _value_chain(self, x: torch.Tensor, keep: bool):
-        """Hidden activations H_1..H_L (panel format; only the last one if not keep) and y (m × out)."""
-        lib, dev, f, m = native.load(), self.device, self.width, x.shape[0]
-        hs = []
+    def _chain(self, first, m, wide, out_w, out_b, out_dim, keep_all, keep_last):
+        """thin input layer -> wide layers -> thin output layer. `first(panel)` launches the thin input kernel into the
+        panel; wide = [(packed weights, bias or None, mode, mask panel or None)]; the LAST wide layer runs with the thin
+        output layer fused into its epilogue (`sb_mlp_gemm_out`) and writes its own activations only if keep_last.
+        Returns (kept panels, y (m × out_dim))."""
+        lib, dev, f = native.load(), self.device, self.width
+        kept = []
+        y = torch.empty(m, out_dim, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
-            h = _Panel(m, f, dev)
-            _check(lib.sb_mlp_thin_in(x.data_ptr(), m, self.in_dim, self.w_in.data_ptr(), self.b_in.data_ptr(), None, f,
-                                      RELU, h.ptr(), _stream(dev)), "sb_mlp_thin_in")
-            hs.append(h)
-            for pk, _, b in self.hidden:
-                nxt = _Panel(m, f, dev)
-                _check(lib.sb_mlp_gemm(h.ptr(), m, f, pk.data_ptr(), f, b.data_ptr(), None, RELU, nxt.ptr(), _stream(dev)),
-                       "sb_mlp_gemm")
-                h = nxt
-                if keep:
-                    hs.append(h)
+            cur = _Panel(m, f, dev)
+            first(cur)
+            if keep_all or (keep_last and not wide):
+                kept.append(cur)
+            for i, (pk, bias, mode, mask) in enumerate(wide):
+                last = i + 1 == len(wide)
+                want_panel = keep_all or not last or keep_last
+                nxt = _Panel(m, f, dev) if want_panel else None
+                args = (cur.ptr(), m, f, pk.data_ptr(), f, native._ptr(bias), mask.ptr() if mask is not None else None, mode,
+                        nxt.ptr() if nxt is not None else None)
+                if last:
+                    scratch = torch.empty(int(lib.sb_mlp_partials_bytes(m, f, out_dim)) // 4, dtype=torch.float32, device=dev)
+                    _check(lib.sb_mlp_gemm_out(*args, out_w.data_ptr(), native._ptr(out_b), out_dim, scratch.data_ptr(),
+                                               y.data_ptr(), _stream(dev)), "sb_mlp_gemm_out")
                 else:
-                    hs[0] = h
-            y = torch.empty(m, self.out_dim, dtype=torch.float32, device=dev)
-            _check(lib.sb_mlp_thin_out(h.ptr(), m, f, self.w_out.data_ptr(), self.b_out.data_ptr(), self.out_dim,
-                                       y.data_ptr(), _stream(dev)), "sb_mlp_thin_out")
-        return hs, y
+                    _check(lib.sb_mlp_gemm(*args, _stream(dev)), "sb_mlp_gemm")
+                if nxt is not None:
+                    cur = nxt
+                    if keep_all or (last and keep_last):
+                        kept.append(cur)
+            if not wide:        # no wide layer at all: the thin output kernel reads the first panel
+                _check(lib.sb_mlp_thin_out(cur.ptr(), m, f, out_w.data_ptr(), native._ptr(out_b), out_dim, y.data_ptr(),
+                                           _stream(dev)), "sb_mlp_thin_out")
+        return kept, y
+
+    def _value_chain(self, x: torch.Tensor, keep: bool):
+        """Hidden activations H_1..H_L (panel format; none if not keep) and y (m × out)."""
+        lib, dev, f, m = native.load(), self.device, self.width, x.shape[0]
+
+        def first(panel):
+            _check(lib.sb_mlp_thin_in(x.data_ptr(), m, self.in_dim, self.w_in.data_ptr(), self.b_in.data_ptr(), None, f,
+                                      RELU, panel.ptr(), _stream(dev)), "sb_mlp_thin_in")
+        wide = [(pk, b, RELU, None) for pk, _, b in self.hidden]
+        return self._chain(first, m, wide, self.w_out, self.b_out, self.out_dim, keep_all=keep, keep_last=keep)
 
     def _tangent_chain(self, t: torch.Tensor, hs) -> torch.Tensor:
         """J(x)·t with the ReLU masks of the value chain's activations hs."""
         lib, dev, f, m = native.load(), self.device, self.width, t.shape[0]
-        with torch.cuda.device(dev):
-            cur = _Panel(m, f, dev)
+
+        def first(panel):
             _check(lib.sb_mlp_thin_in(t.data_ptr(), m, self.in_dim, self.w_in.data_ptr(), None, hs[0].ptr(), f, MASK,
-                                      cur.ptr(), _stream(dev)), "sb_mlp_thin_in")
-            for (pk, _, _), h in zip(self.hidden, hs[1:]):
-                nxt = _Panel(m, f, dev)
-                _check(lib.sb_mlp_gemm(cur.ptr(), m, f, pk.data_ptr(), f, None, h.ptr(), MASK, nxt.ptr(), _stream(dev)),
-                       "sb_mlp_gemm")
-                cur = nxt
-            jt = torch.empty(m, self.out_dim, dtype=torch.float32, device=dev)
-            _check(lib.sb_mlp_thin_out(cur.ptr(), m, f, self.w_out.data_ptr(), None, self.out_dim, jt.data_ptr(),
-                                       _stream(dev)), "sb_mlp_thin_out")
-        return jt
+                                      panel.ptr(), _stream(dev)), "sb_mlp_thin_in")
+        wide = [(pk, None, MASK, h) for (pk, _, _), h in zip(self.hidden, hs[1:])]
+        return self._chain(first, m, wide, self.w_out, None, self.out_dim, keep_all=False, keep_last=False)[1]
 
     def _transpose_chain(self, g: torch.Tensor, hs) -> torch.Tensor:
         """J(x)ᵀ·g (m × in) for a cotangent g (m × out)."""
         lib, dev, f, m = native.load(), self.device, self.width, g.shape[0]
-        with torch.cuda.device(dev):
-            cur = _Panel(m, f, dev)
+
+        def first(panel):
             _check(lib.sb_mlp_thin_in(g.data_ptr(), m, self.out_dim, self.w_out_t.data_ptr(), None, hs[-1].ptr(), f, MASK,
-                                      cur.ptr(), _stream(dev)), "sb_mlp_thin_in")
-            for (_, pk_t, _), h in zip(reversed(self.hidden), reversed(hs[:-1])):
-                nxt = _Panel(m, f, dev)
-                _check(lib.sb_mlp_gemm(cur.ptr(), m, f, pk_t.data_ptr(), f, None, h.ptr(), MASK, nxt.ptr(), _stream(dev)),
-                       "sb_mlp_gemm")
-                cur = nxt
-            gx = torch.empty(m, self.in_dim, dtype=torch.float32, device=dev)
-            _check(lib.sb_mlp_thin_out(cur.ptr(), m, f, self.w_in_t.data_ptr(), None, self.in_dim, gx.data_ptr(),
-                                       _stream(dev)), "sb_mlp_thin_out")
-        return gx
+                                      panel.ptr(), _stream(dev)), "sb_mlp_thin_in")
+        wide = [(pk_t, None, MASK, h) for (_, pk_t, _), h in zip(reversed(self.hidden), reversed(hs[:-1]))]
+        return self._chain(first, m, wide, self.w_in_t, None, self.in_dim, keep_all=False, keep_last=False)[1]
 
     # ---- public operators ----
     def _rows(self, x: torch.Tensor, name: str) -> torch.Tensor:

@@ -88,6 +88,9 @@ _SIGNATURES = {
     "sb_mlp_thin_out": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "sb_mlp_gemm": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p,
                             c_void_p]),
+    "sb_mlp_partials_bytes": (c_int64, [c_int64, c_int, c_int]),
+    "sb_mlp_gemm_out": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p,
+                                c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "sb_debug_trace": (None, [c_void_p]),
     "sb_fp32_peak": (c_int, [c_int, c_int, POINTER(c_double), c_void_p]),
 }

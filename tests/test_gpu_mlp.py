@@ -355,3 +355,37 @@ def test_wide_layer_kernel_rectangular(mlp, k, n):
     native._check(lib.sb_mlp_pack_weights(wt.data_ptr(), n, k, 1, pk.data_ptr(), s), "pack")
     native._check(lib.sb_mlp_gemm(pa.ptr(), m, k, pk.data_ptr(), n, None, None, 0, pc.ptr(), s), "gemm")
     assert rel(pc.to_rows(), a.double() @ w.double().t()) < 1e-5
+
+
+@pytest.mark.parametrize("m,out_dim", [(300, 2), (2500, 3), (40000, 2), (1000, 8)])
+def test_fused_thin_output_layer(mlp, m, out_dim, monkeypatch):
+    """sb_mlp_gemm_out: y = relu(A·Wᵀ + b)·W_outᵀ + b_out from the wide layer's epilogue, with and without the wide
+    activations written; y is bitwise independent of the tile schedule (narrow last round or not) because the partial
+    products are formed per 64-column granule and added in granule order."""
+    from sindy_b200 import native
+    lib = native.load()
+    g = torch.Generator(device="cuda").manual_seed(m + out_dim)
+    f = 512
+    a = torch.randn(m, f, device="cuda", generator=g)
+    w = torch.randn(f, f, device="cuda", generator=g) / f ** 0.5
+    b = torch.randn(f, device="cuda", generator=g)
+    w_out = torch.randn(out_dim, f, device="cuda", generator=g) / f ** 0.5
+    b_out = torch.randn(out_dim, device="cuda", generator=g)
+    s = native._stream(a.device)
+    pa, pc = mlp._Panel.from_rows(a), mlp._Panel(m, f, a.device)
+    pk = torch.empty(2 * f * f, device="cuda")
+    native._check(lib.sb_mlp_pack_weights(w.data_ptr(), f, f, 0, pk.data_ptr(), s), "pack")
+    scratch = torch.empty(int(lib.sb_mlp_partials_bytes(m, f, out_dim)) // 4, device="cuda")
+    ys = []
+    for narrow, with_panel in (("1", True), ("1", False), ("0", False)):
+        monkeypatch.setenv("SB_MLP_NARROW", narrow)
+        y = torch.full((m, out_dim), float("nan"), device="cuda")
+        scratch.fill_(float("nan"))
+        native._check(lib.sb_mlp_gemm_out(pa.ptr(), m, f, pk.data_ptr(), f, b.data_ptr(), None, 1,
+                                          pc.ptr() if with_panel else None, w_out.data_ptr(), b_out.data_ptr(), out_dim,
+                                          scratch.data_ptr(), y.data_ptr(), s), "gemm_out")
+        ys.append(y)
+    h = torch.relu(a.double() @ w.double().t() + b.double())
+    assert rel(ys[0], h @ w_out.double().t() + b_out.double()) < 1e-5
+    assert rel(pc.to_rows(), h) < 1e-5
+    assert torch.equal(ys[0], ys[1]) and torch.equal(ys[0], ys[2])
