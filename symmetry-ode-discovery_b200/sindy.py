@@ -287,6 +287,44 @@ def _min_norm_solve(H: torch.Tensor, rhs: torch.Tensor, rcond: float) -> torch.T
     return scale * (U @ (inv * (U.T @ (scale * rhs))))
 
 
+def _masked_solve_batched(H, b, mask, rcond):
+    """The solves of `_min_norm_solve` for the d equations at once: equation i solves H[m_i, m_i]·ξ = b[m_i, i] on its
+    support m_i = mask[i]. Same equilibration, same rank rule (threshold relative to the largest eigenvalue over ALL
+    equations, dimension = number of live coefficients — K when every coefficient is live, as the reference then solves
+    one K×K system with d right-hand sides). Returns Ξ (d × K, fp64), zero off the support."""
+    d, K = mask.shape
+    M = mask.to(H.dtype)
+    if rcond > 0.0:
+        scale = torch.ones(K, dtype=H.dtype, device=H.device)
+    else:
+        diag = torch.diagonal(H)
+        scale = torch.where(diag > 0, diag.clamp_min(torch.finfo(H.dtype).tiny).rsqrt(), torch.zeros_like(diag))
+    Hs = H * scale.unsqueeze(0) * scale.unsqueeze(1)
+    Hb = M.unsqueeze(2) * Hs.unsqueeze(0) * M.unsqueeze(1)
+    rhs = (scale.unsqueeze(1) * b).T * M                                   # d × K
+    if rcond > 0.0:
+        cut = rcond * rcond
+    else:
+        n_live = M.sum()
+        cut = torch.where(n_live == d * K, torch.full_like(n_live, float(K)), n_live) * torch.finfo(H.dtype).eps
+        # Fast path for the full-rank case, which is every well-posed fit: Cholesky of the equilibrated blocks (dead
+        # coordinates padded with ones). λ_min ≥ 1/‖L⁻¹‖_F² and λ_max ≤ K (unit diagonal), so when the bound clears the
+        # rank rule's threshold no direction would have been dropped and the Cholesky solution IS the min-norm solution;
+        # a 56 × 56 fp64 syevd costs ~0.6 ms on the device, nine of them per `solve_SINDy`, the batched Cholesky ~0.1.
+        L, info = torch.linalg.cholesky_ex(Hb + torch.diag_embed(1.0 - M))
+        Linv = torch.linalg.solve_triangular(L, torch.eye(K, dtype=H.dtype, device=H.device).expand(d, K, K), upper=False)
+        lam_min_bound = 1.0 / (Linv * Linv).sum(dim=(-1, -2)).clamp_min(torch.finfo(H.dtype).tiny)
+        full_rank = (info == 0).all() & (lam_min_bound.min() > cut * K) & torch.isfinite(Linv).all()
+        if bool(full_rank):                                                # one host sync (the loop has one per step anyway)
+            sol = torch.cholesky_solve(rhs.unsqueeze(-1), L).squeeze(-1)
+            return sol * scale * M
+    lam, U = torch.linalg.eigh(Hb)
+    keep = lam > cut * lam.max().clamp_min(0)
+    inv = torch.where(keep, 1.0 / lam.clamp_min(torch.finfo(lam.dtype).tiny), torch.zeros_like(lam))
+    proj = torch.matmul(U.transpose(-1, -2), rhs.unsqueeze(-1)).squeeze(-1)
+    return torch.matmul(U, (inv * proj).unsqueeze(-1)).squeeze(-1) * scale * M
+
+
 def _stlsq_update(regressor, G, b, ridge, n_rows, st_threshold, driver='gels'):
     """Shared tail of solve_SINDy_one_step / WSINDyWrapper.solve: solve on the current support, write the
     parameters back, threshold, report convergence. G (K×K) and b (K×d) are fp64 normal-equation blocks;
@@ -302,9 +340,11 @@ def _stlsq_update(regressor, G, b, ridge, n_rows, st_threshold, driver='gels'):
     rcond = float(torch.finfo(torch.float32).eps) * min(max(n_rows, K), 1 << 14) if driver == 'gelsy' else 0.0
     prev_mask = regressor.mask.clone()
 
-    if bool(torch.all(mask)) and not regressor.constraint:
-        sol = _min_norm_solve(H, b, rcond)                       # K×d
-        regressor.Xi.data = sol.T.to(torch.float32).contiguous()
+    if not regressor.constraint:
+        # d independent systems on the supports of the d equations, solved as ONE batch of K×K problems with the
+        # masked-out rows and columns zeroed (their eigenvalues are zero and are dropped by the rank rule): no index
+        # lists, no host synchronisation, and 3 eigenproblems of size K instead of one of size d·K
+        regressor.Xi.data = _masked_solve_batched(H, b, mask, rcond).to(torch.float32).contiguous()
     else:
         flat_mask = mask.flatten()                               # equation-major: i*K + k
         idx = torch.nonzero(flat_mask, as_tuple=False).flatten()
@@ -312,30 +352,24 @@ def _stlsq_update(regressor, G, b, ridge, n_rows, st_threshold, driver='gels'):
         # (I_d ⊗ H)[m, m]: zero between different equations
         Hm = H[col][:, col] * (eq.unsqueeze(1) == eq.unsqueeze(0)).to(H.dtype)
         rhs = b.T.reshape(-1)[idx]
-        if regressor.constraint:
-            Q = regressor.Q.to(torch.float64)
-            if regressor.allow_constant:
-                extra = torch.zeros((Q.shape[0], d), dtype=Q.dtype, device=dev)
-                for i in range(d):
-                    extra[i * Q.shape[0] // d, i] = 1.0
-                Q = torch.cat([Q, extra], dim=1)
-            Qm = Q[idx]
-            effective = torch.any(Qm != 0.0, dim=0)              # drop parameters that touch no live column
-            Qe = Qm[:, effective]
-            sol = _min_norm_solve(Qe.T @ Hm @ Qe, Qe.T @ rhs, rcond)
-            full = torch.zeros(Q.shape[1], dtype=torch.float64, device=dev)
-            full[effective] = sol
-            full = full.to(torch.float32)
-            if regressor.allow_constant:
-                regressor.beta.data = full[:-d].contiguous()
-                regressor.const.data = full[-d:].view(-1, 1).contiguous()
-            else:
-                regressor.beta.data = full
+        Q = regressor.Q.to(torch.float64)
+        if regressor.allow_constant:
+            extra = torch.zeros((Q.shape[0], d), dtype=Q.dtype, device=dev)
+            for i in range(d):
+                extra[i * Q.shape[0] // d, i] = 1.0
+            Q = torch.cat([Q, extra], dim=1)
+        Qm = Q[idx]
+        effective = torch.any(Qm != 0.0, dim=0)              # drop parameters that touch no live column
+        Qe = Qm[:, effective]
+        sol = _min_norm_solve(Qe.T @ Hm @ Qe, Qe.T @ rhs, rcond)
+        full = torch.zeros(Q.shape[1], dtype=torch.float64, device=dev)
+        full[effective] = sol
+        full = full.to(torch.float32)
+        if regressor.allow_constant:
+            regressor.beta.data = full[:-d].contiguous()
+            regressor.const.data = full[-d:].view(-1, 1).contiguous()
         else:
-            sol = _min_norm_solve(Hm, rhs, rcond)
-            coef = torch.zeros(d * K, dtype=torch.float32, device=dev)
-            coef[idx] = sol.to(torch.float32)
-            regressor.Xi.data = coef.view(d, K)
+            regressor.beta.data = full
     regressor.set_threshold(st_threshold)
     return torch.allclose(prev_mask, regressor.mask)
 

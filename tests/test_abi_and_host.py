@@ -489,3 +489,34 @@ def test_frozen_autoencoder_folding_reproduces_the_module():
     assert mlp.accelerate(ae) is None                                # CPU module: the PyTorch path stays
     ae.decoder[1] = torch.nn.Tanh()
     assert mlp.fold_layers(ae.decoder) is None
+
+
+def test_batched_masked_solve_equals_the_block_diagonal_system():
+    """`sindy._masked_solve_batched` (d eigenproblems of size K, masked rows/columns zeroed) against the formulation it
+    replaces — one min-norm solve of the block-diagonal system (I_d ⊗ H)[m, m] — for both rank rules, full masks, ragged
+    masks, an empty equation and an exactly singular Gram."""
+    import torch
+    import sindy
+    g = torch.Generator().manual_seed(0)
+    d, K = 3, 20
+    A = torch.randn(400, K, dtype=torch.float64, generator=g) * torch.logspace(-2, 2, K, dtype=torch.float64)
+    A[:, 7] = A[:, 3] * 2.0                                              # exactly dependent columns
+    H = A.T @ A
+    b = A.T @ torch.randn(400, d, dtype=torch.float64, generator=g)
+    masks = [torch.ones(d, K, dtype=torch.bool), torch.rand(d, K, generator=g) > 0.4, torch.rand(d, K, generator=g) > 0.8]
+    masks[2][1] = False                                                  # an equation with no live column
+    for mask in masks:
+        for rcond in (0.0, 2e-3):
+            got = sindy._masked_solve_batched(H, b, mask, rcond)
+            if bool(mask.all()):
+                want = sindy._min_norm_solve(H, b, rcond).T
+            else:
+                idx = torch.nonzero(mask.flatten()).flatten()
+                eq, col = idx // K, idx % K
+                Hm = H[col][:, col] * (eq.unsqueeze(1) == eq.unsqueeze(0)).to(H.dtype)
+                sol = sindy._min_norm_solve(Hm, b.T.reshape(-1)[idx], rcond)
+                want = torch.zeros(d * K, dtype=torch.float64)
+                want[idx] = sol
+                want = want.view(d, K)
+            assert torch.equal(got != 0, want != 0) or bool(((got != 0) <= mask).all())
+            assert float((got - want).abs().max()) <= 1e-9 * float(want.abs().max().clamp_min(1e-30)), (rcond, mask.sum())
