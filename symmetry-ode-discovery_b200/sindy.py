@@ -316,7 +316,10 @@ def _masked_solve_batched(H, b, mask, rcond):
         lam_min_bound = 1.0 / (Linv * Linv).sum(dim=(-1, -2)).clamp_min(torch.finfo(H.dtype).tiny)
         full_rank = (info == 0).all() & (lam_min_bound.min() > cut * K) & torch.isfinite(Linv).all()
         if bool(full_rank):                                                # one host sync (the loop has one per step anyway)
-            sol = torch.cholesky_solve(rhs.unsqueeze(-1), L).squeeze(-1)
+            # two triangular solves (cuBLAS trsm); `torch.cholesky_solve` costs ~1 s of solver-library start-up on its
+            # first call, a third of a whole `main_wsindy.py` run on the test fixture
+            y = torch.linalg.solve_triangular(L, rhs.unsqueeze(-1), upper=False)
+            sol = torch.linalg.solve_triangular(L.transpose(-1, -2), y, upper=True).squeeze(-1)
             return sol * scale * M
     lam, U = torch.linalg.eigh(Hb)
     keep = lam > cut * lam.max().clamp_min(0)
