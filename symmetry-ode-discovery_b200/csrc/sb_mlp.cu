@@ -16,9 +16,13 @@
 // no tensor maps — and the epilogue of one layer writes the next layer's operand directly (split included).
 //   warp 0: bulk-copy producer (one lane), 4-stage ring        warp 1: MMA issuer (one lane), 6 MMAs of
 //   128 × 256 × 8 per stage, `tcgen05.commit` to the stage's empty barrier and to the accumulator's full barrier
-//   warps 2-9: epilogue (two per TMEM lane quarter) — `tcgen05.ld` 16 columns at a time, bias / ReLU / mask, split, 16-byte stores that are
-//   128-byte contiguous per 8 lanes. Two 256-column accumulators in TMEM: the epilogue of tile i overlaps the main loop
-//   of tile i+1.
+//   warps 2-9: epilogue (two per TMEM lane quarter) — `tcgen05.ld` 16 columns at a time, bias / ReLU / mask, split,
+//   16-byte stores that are 128-byte contiguous per 8 lanes.
+// TMEM holds TWO 256-column accumulators of one tile: the large products (A_hi·B_hi) and the small ones, added by the
+// epilogue in fp32 round-to-nearest (the tensor core's accumulator truncates; see the SPLIT comment). The last partial
+// round of tiles runs as narrower pieces (runtime N), and the thin OUTPUT layer of a chain can be fused into the
+// epilogue (`w_out`: per-granule partial products, summed in granule order by `mlp_sum_partials_kernel`).
+// `mlp_gemm_pair_kernel`: the same tile loop on a CTA pair (`cta_group::2`), kept as a measured A/B variant.
 // `mlp_in_kernel` / `mlp_out_kernel`: the thin first / last layers (2 → 512, 512 → 2 and their transposes) on CUDA
 // cores, writing / reading the panel format. `mlp_pack_*`: format conversions (weights once per fit).
 #include <stdlib.h>
