@@ -16,7 +16,10 @@ this repo's module directory has been put first and the reference's directory se
 
 Options (before the script): `--reference DIR` (default: the script's directory, else $SINDY_B200_REFERENCE, else
 <repo>/baseline/_ref), `--reference-train` (keep the reference's own `train.py`: its loops then run operator by operator
-on this repo's `sindy` / `model_utils` through autograd), `--where` (print where the hot-path modules resolve, and exit).
+on this repo's `sindy` / `model_utils` through autograd), `--where` (print where the hot-path modules resolve, and exit),
+`--seeds A-B[,C...]` (run the script once per seed IN THIS PROCESS with `--seed k` appended: what `run_scripts/*.sh` does
+with one interpreter start — ≈8 s of imports and CUDA start-up — per seed; any cfg, the runs stay independent and write
+the same `eval_results/<save_dir>/seed<k>.npz`; `sweep_main.py` goes further for the cfgs it can batch).
 """
 from __future__ import annotations
 
@@ -88,15 +91,27 @@ def use_reference_train(reference):
     return mod
 
 
+def parse_seeds(spec):
+    """'0-49', '3', '0-4,10,20-22' -> list of ints."""
+    out = []
+    for part in spec.split(","):
+        lo, _, hi = part.partition("-")
+        out.extend(range(int(lo), int(hi or lo) + 1))
+    return out
+
+
 def main(argv=None):
     argv = list(sys.argv[1:] if argv is None else argv)
     reference, ref_train, show = None, False, False
-    while argv and argv[0] in ("--reference", "--reference-train", "--where"):
+    seeds = None
+    while argv and argv[0] in ("--reference", "--reference-train", "--where", "--seeds"):
         opt = argv.pop(0)
         if opt == "--reference":
             reference = argv.pop(0)
         elif opt == "--reference-train":
             ref_train = True
+        elif opt == "--seeds":
+            seeds = parse_seeds(argv.pop(0))
         else:
             show = True
     as_module = bool(argv) and argv[0] == "-m"
@@ -120,11 +135,12 @@ def main(argv=None):
             return 0
     if ref_train:
         use_reference_train(reference)
-    sys.argv = [target] + argv[1:]
-    if as_module:
-        runpy.run_module(target, run_name="__main__", alter_sys=True)
-    else:
-        runpy.run_path(target, run_name="__main__")
+    for seed in (seeds if seeds is not None else [None]):
+        sys.argv = [target] + argv[1:] + ([] if seed is None else ["--seed", str(seed)])
+        if as_module:
+            runpy.run_module(target, run_name="__main__", alter_sys=True)
+        else:
+            runpy.run_path(target, run_name="__main__")
     return 0
 
 

@@ -520,3 +520,23 @@ def test_batched_masked_solve_equals_the_block_diagonal_system():
                 want = want.view(d, K)
             assert torch.equal(got != 0, want != 0) or bool(((got != 0) <= mask).all())
             assert float((got - want).abs().max()) <= 1e-9 * float(want.abs().max().clamp_min(1e-30)), (rcond, mask.sum())
+
+
+def test_launcher_seed_loop_runs_the_script_once_per_seed_in_one_process(tmp_path):
+    """`run.py --seeds 3-5,9 script.py --x 1` executes the script four times in ONE interpreter with `--seed k` appended
+    (the replacement for run_scripts/*.sh's 50 interpreter starts)."""
+    import subprocess
+    import sys
+    import config_runs
+    ref = config_runs.find_reference()
+    if ref is None:
+        pytest.skip("no reference checkout")
+    script = tmp_path / "probe.py"
+    script.write_text("import os, sys\nprint('RUN', os.getpid(), sys.argv[1:])\n")
+    launcher = os.path.join(ROOT, "symmetry-ode-discovery_b200", "sindy_b200", "run.py")
+    out = subprocess.run([sys.executable, launcher, "--reference", ref, "--seeds", "3-5,9", str(script), "--x", "1"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    runs = [l for l in out.stdout.splitlines() if l.startswith("RUN")]
+    assert [r.split(" ", 2)[2] for r in runs] == [str(["--x", "1", "--seed", str(k)]) for k in (3, 4, 5, 9)]
+    assert len({r.split()[1] for r in runs}) == 1
