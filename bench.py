@@ -706,6 +706,22 @@ def extras(native, dev, peaks, fp32_peak):
         out[f"train_step_d{d}_p{p}_K{lib.K}"] = {"samples_per_s": n / (ms * 1e-3), "ms": ms, "hbm_gbs": gbs,
                                                  "hbm_frac": gbs / peaks["hbm_gbs"]}
         del x, dx
+    # the GENERIC runtime-table kernels (every library without a specialisation, here (2, 3) + sine, K = 14): parity-complete,
+    # not tuned — timed so that the distance to the specialised kernels is on record
+    try:
+        n_g = 10 ** 7
+        lg = native.Library(2, 3, True, False)
+        xg = torch.rand(n_g, 2, device=dev, generator=gen) * 2 - 1
+        dxg = torch.randn(n_g, 2, device=dev, generator=gen)
+        Wg = torch.randn(2, lg.K, device=dev, generator=gen)
+        og = torch.empty(lg.step_out_len(3), dtype=torch.float64, device=dev)
+        ms = timed(lambda: native.train_step(xg, dxg, Wg, lg, 3, out=og))
+        out["train_step_generic_d2_p3_sine_K14_1e7"] = {"samples_per_s": n_g / (ms * 1e-3), "ms": ms,
+                                                         "hbm_gbs": 16 * n_g / (ms * 1e-3) / 1e9,
+                                                         "variant": native.train_step_variant(lg, 3)}
+        del xg, dxg
+    except Exception as exc:   # noqa: BLE001
+        out["train_step_generic_d2_p3_sine_K14_1e7"] = {"error": repr(exc)}
     # the C5 step with the linear so(3) Lie-derivative regulariser (weight 0.1, `train.py:503-507`): closure kernel +
     # power-sum Gram kernel (second pass over x) + K×K algebra, replayed as one CUDA graph; and the STLSQ data pass
     from sindy_b200.dist import ShardedTrainStep
