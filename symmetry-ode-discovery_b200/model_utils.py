@@ -58,7 +58,9 @@ class EulerFlowMap:
         return reg.Xi * reg.mask
 
     def __call__(self, x):
-        if self._fused(x) and not (torch.is_grad_enabled() and x.requires_grad):
+        # first-order differentiable in x and Ξ (one launch forward, one backward); a caller that differentiates THROUGH
+        # the backward (torch.autograd.functional.jvp's double vjp) must use `.jvp` or a plain closure over `odeint`
+        if self._fused(x):
             return ops.euler_flow(x, None, self._w(), self.regressor.library, self.dt, self.n_steps)[0]
         return odeint(self.regressor, x, self.t, self.dt)
 

@@ -552,6 +552,12 @@ def test_golden_symmreg(nat, golden):
         reg.zero_grad(); li.backward()
         assert abs(float(li) - float(g[tag + "_li"])) < 1e-4 * float(g[tag + "_li"])
         assert rel(reg.Xi.grad, g[tag + "_gi"]) < 5e-4
+        # symmreg_f evaluates f at g(x), which carries a gradient: the fused flow map differentiates with respect to x too
+        x_fx = torch.stack([x, flow(x)], dim=1)
+        lf2 = model_utils.symmreg_f(x_fx, ae, gen, f=flow, require_grad=True)
+        reg.zero_grad(); lf2.backward()
+        assert abs(float(lf2) - float(g[tag + "_lf"])) < 2e-4 * float(g[tag + "_lf"])
+        assert rel(reg.Xi.grad, g[tag + "_gf"]) < 1e-3
         # g(x) and the TRUE J_g(x) computed once per fit, then the streaming kernel per closure == symmreg_r
         gx2, Jgx2 = model_utils.group_action_and_jacobian(x, ae, gen)
         assert rel(torch.stack(gx2), g[tag + "_gx"]) < 1e-5 and rel(torch.stack(Jgx2), g[tag + "_Jgx"]) < 1e-4
