@@ -16,7 +16,7 @@
 // no tensor maps — and the epilogue of one layer writes the next layer's operand directly (split included).
 //   warp 0: bulk-copy producer (one lane), 4-stage ring        warp 1: MMA issuer (one lane), 6 MMAs of
 //   128 × 256 × 8 per stage, `tcgen05.commit` to the stage's empty barrier and to the accumulator's full barrier
-//   warps 2-9: epilogue (two per TMEM lane quarter) — `tcgen05.ld` 16 columns at a time, bias / ReLU / mask, split,
+//   warps 2-17: epilogue (four per TMEM lane quarter, 64 columns each) — `tcgen05.ld` 16 columns at a time, bias / ReLU / mask, split,
 //   16-byte stores that are 128-byte contiguous per 8 lanes.
 // TMEM holds TWO 256-column accumulators of one tile: the large products (A_hi·B_hi) and the small ones, added by the
 // epilogue in fp32 round-to-nearest (the tensor core's accumulator truncates; see the SPLIT comment). The last partial
@@ -41,7 +41,7 @@ constexpr uint32_t kBBlock = kBN * kBK * 4;                    // 16 KB: hi or l
 constexpr uint32_t kStageBytes = 2 * kABlock + 2 * kBBlock;    // 48 KB
 constexpr uint32_t kLBO = 128;                                 // bytes between core matrices adjacent along K
 constexpr uint32_t kSBO = (kBK / 4) * 128;                     // bytes between 8-row groups
-constexpr int kEpiWarps = 8;                                   // two per TMEM lane quarter, 128 columns each
+constexpr int kEpiWarps = 16;                                  // four per TMEM lane quarter, 64 columns each
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr uint32_t kTmemCols = 512;
 constexpr size_t kSmem = 1024 + (size_t)kStages * kStageBytes + 256;
