@@ -678,7 +678,7 @@ int small_variant() {
   if (v < 0) {
     const char* e = getenv("SB_FUSED_VARIANT_SMALL");
     v = e ? atoi(e) : 0;                       // 0 = per-shape default
-    if (v != 5 && v != 13 && v != 37 && v != 45) v = 0;
+    if (v != 5 && v != 13 && v != 37 && v != 45 && v != 21 && v != 53) v = 0;
     cached.store(v, std::memory_order_release);
   }
   return v;
@@ -753,11 +753,16 @@ int launch_fused(const FusedArgs& a, void* ws, int64_t ws_bytes, cudaStream_t s,
   // tried on the 2048x3 ring: (2,3) 0.327, (3,3) 0.686 — slower (170 registers, the second expansion competes for the
   // same FMA pipe); removed. A 2048 x 2 ring (room for a second resident CTA at d = 3: 16 warps per SM instead of 8) is
   // a wash: (3,3) 0.556 against 0.560, (2,3) 0.322 against 0.290 — occupancy is not what limits these shapes; removed.
-  const int chosen = small_variant() ? small_variant() : ((D == 2 && P == 3) ? 45 : 13);
+  // Round 2, later: 4096-sample tiles (16 samples per thread and tile, one resident CTA) beat both — (2,3) 0.2921 ->
+  // 0.2831 with prefetch (variant 53; 0.3184 without), (3,3) 0.5624 -> 0.5329 without (variant 21; 0.5552 with), (2,2)
+  // 0.2634 -> 0.2744 / 0.2667 (stays on 2048 x 3); a third 4096-sample stage at d = 2 changes nothing (0.2826 / 0.2599).
+  const int chosen = small_variant() ? small_variant() : ((D == 2 && P == 3) ? 53 : ((D == 3 && P == 3) ? 21 : 13));
   switch (chosen) {
     case 13: return launch_fused_var<D, P, LEFT, 13>(a, ws, ws_bytes, s, slot);   // 2048 x 3 ring
     case 37: return launch_fused_var<D, P, LEFT, 37>(a, ws, ws_bytes, s, slot);   // 1024 x 4 ring + next-sample prefetch
     case 45: return launch_fused_var<D, P, LEFT, 45>(a, ws, ws_bytes, s, slot);   // 2048 x 3 ring + prefetch
+    case 21: return launch_fused_var<D, P, LEFT, 21>(a, ws, ws_bytes, s, slot);   // 4096 x 2 ring
+    case 53: return launch_fused_var<D, P, LEFT, 53>(a, ws, ws_bytes, s, slot);   // 4096 x 2 ring + prefetch
     default: return launch_fused_var<D, P, LEFT, 5>(a, ws, ws_bytes, s, slot);
   }
 }
