@@ -25,7 +25,7 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kTile = 2048;  // samples per stage (x only)
+constexpr int kTile = 2048;  // samples per stage (x only); 4096 x 2 measured slower (K = 56: 1.70 against 1.59 ms)
 constexpr int kStages = 4;
 
 constexpr int trailing_len(int dt, int deg) { return deg < 0 ? 0 : n_poly_terms(dt, deg); }
