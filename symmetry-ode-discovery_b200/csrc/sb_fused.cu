@@ -903,7 +903,7 @@ __global__ void __launch_bounds__(256) forward_spec_kernel(const float* __restri
 // grid-stride kernel waiting on its own global loads (long scoreboard 4.97 per issue, FMA pipe 73.6 % active) even with
 // the next sample requested one iteration ahead. Persistent CTAs, tiles dealt round-robin, y written straight from
 // registers (a warp's 32 samples are 32·d contiguous floats).
-constexpr int kFwdTile = 2048, kFwdStages = 3, kFwdThreads = 256;
+constexpr int kFwdTile = 2048, kFwdStages = 3, kFwdThreads = 256;   // 4096 x 2: within 1 % (0.784 / 0.441 / 0.310 ms)
 
 template <int D, int P>
 __global__ void __launch_bounds__(kFwdThreads, 2) forward_tma_kernel(const float* __restrict__ x, int64_t n,
