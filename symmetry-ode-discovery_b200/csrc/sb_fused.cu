@@ -664,7 +664,8 @@ int tuning_variant() {
     // and so is a packed-monomial schedule (23 mul.f32x2 + 6 FMUL instead of 52 FMUL, same bits): 1.367 ms against
     // 1.342 — a scalar FMUL holds the FMA pipe one cycle, a packed one two, so packing only saves issue slots. Reading
     // only x of the next sample ahead (3 registers; its LDS shows as the loop's largest short-scoreboard stall) made no
-    // difference either: 1.3325 against 1.3300.
+    // difference either: 1.3325 against 1.3300. Later (whole fit step at N = 1e8): refilling the stage consumed TWO tiles ago
+    // (bit 6) 1.3008 against 1.3011, with a fourth 2048-sample stage 1.348; 4096 x 2 tiles 1.3124 — the ring is not it.
     v = e ? atoi(e) : 15;
     if (v < 0 || v > 1023) v = 15;
     cached.store(v, std::memory_order_release);
