@@ -726,6 +726,11 @@ int launch_fused_var(FusedArgs a, void* ws, int64_t ws_bytes, cudaStream_t s, in
   a.ticket = reinterpret_cast<unsigned int*>(ws);
   a.partial = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + kWsHeaderBytes);
   a.trace = g_trace;
+  // Programmatic dependent launch between consecutive iterations was tried (griddepcontrol.launch_dependents / .wait
+  // after the first tile is in flight, cudaLaunchAttributeProgrammaticStreamSerialization): 173.11 -> 172.84 us per
+  // iteration at the 8-GPU shard size, 1298.95 -> 1298.11 at N = 1e8 — the SM that hosts the predecessor's last block
+  // starts last and sets the end of the successor — and the 200-iteration loss history was NO LONGER bitwise the
+  // default's: the successor reads W through the constant bank while the predecessor rewrites the slot. Removed.
   kern<<<(unsigned)grid, C::kThreads, C::kSmemBytes, s>>>(a);
   SB_LAUNCH_CHECK("fused_step_kernel");
   return SB_OK;
