@@ -360,12 +360,22 @@ int wsindy_integrals(const float* x, int64_t n_traj, int64_t T, const LibTab& t,
   const bool poly = !t.sine && !t.exp_;
   // batches take the tensor-core kernel (sb_wsindy_tc.cu: 1.25-2.2x the CUDA-core batched kernel below, measured);
   // SB_WSINDY_TC=0 selects the CUDA-core kernel (A/B, and the more accurate of the two: 1e-6 against 1.5e-5 on G)
-  {
-    const char* e = getenv("SB_WSINDY_TC");
-    if (!(e && e[0] == '0') && T > 0 && n_traj >= kBatchedMinTraj && wsindy_tc_supported(t, n_test))
+  // Which kernel: a batched kernel (tensor-core or CUDA-core) needs a full wave of CTAs whatever the batch size — 0.8-1.2
+  // ms at T = 8000 — while the per-(test function, trajectory) kernel costs 3.6 / 4.9 / 9.1 / 29 us per trajectory at
+  // K = 6 / 10 / 20 / 56 (tools/time_wsindy_small.py): below ≈ min(200, 1700/K) trajectories the simple kernel wins (8
+  // trajectories at K = 10: 0.06 against 0.78 ms). SB_WSINDY_TC overrides: 1 = tensor-core kernel from 8 trajectories on,
+  // 0 = CUDA-core batched kernel, s = per-test-function kernel.
+  const char* e = getenv("SB_WSINDY_TC");
+  const bool force_simple = e && e[0] == 's';
+  const bool force_batched = e && (e[0] == '0' || e[0] == '1');
+  int64_t batched_min = 1700 / (t.K > 0 ? t.K : 1);
+  if (batched_min > 200) batched_min = 200;
+  if (batched_min < kBatchedMinTraj || force_batched) batched_min = kBatchedMinTraj;
+  if (!force_simple) {
+    if (!(e && e[0] == '0') && T > 0 && n_traj >= batched_min && wsindy_tc_supported(t, n_test))
       return wsindy_integrals_tc(x, n_traj, T, t, dt, t_max, n_test, G, b, s);
   }
-  if (poly && T > 0 && n_test <= 64 && n_traj >= kBatchedMinTraj && n_traj <= (int64_t)0x7fffffff * 4) {
+  if (!force_simple && poly && T > 0 && n_test <= 64 && n_traj >= batched_min && n_traj <= (int64_t)0x7fffffff * 4) {
 #define X(D, P) if (t.d == D && t.n_poly == n_poly_terms(D, P)) return launch_batched<D, P>(a, n_traj, s);
     X(2, 2) X(2, 3) X(3, 2) X(3, 3) X(3, 5)
 #undef X

@@ -760,3 +760,18 @@ def test_forward_through_the_bulk_copy_ring_is_bitwise_the_grid_stride_kernel(na
     idx = torch.randint(0, n, (2000,), device="cuda", generator=gen)
     want = O.theta(x[idx].cpu().numpy().astype(np.float64), p, False, bool(e)) @ W.double().cpu().numpy().T
     assert rel(ya[idx], want) < 2e-6
+
+
+def test_wsindy_dispatch_by_batch_size(nat, monkeypatch):
+    """Without SB_WSINDY_TC the kernel is chosen by batch size: a batched kernel needs a full wave of CTAs whatever the
+    batch, so below ≈ min(200, 1700/K) trajectories the per-(test function, trajectory) kernel runs — bitwise what one call
+    per trajectory returns — and larger batches go to the tensor-core kernel (within its 1e-4 of the former)."""
+    monkeypatch.delenv("SB_WSINDY_TC", raising=False)
+    lib = nat.Library(2, 3)
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.rand(260, 500, 2, device="cuda", generator=gen) * 0.8 + 0.2
+    G_small, b_small = nat.wsindy_integrals(x[:20], lib, 0.002, 1.0, 50)
+    one = [nat.wsindy_integrals(x[i:i + 1], lib, 0.002, 1.0, 50) for i in range(20)]
+    assert torch.equal(G_small, torch.cat([g for g, _ in one])) and torch.equal(b_small, torch.cat([b for _, b in one]))
+    G_big, b_big = nat.wsindy_integrals(x, lib, 0.002, 1.0, 50)                  # 260 > 170: batched (tensor-core) kernel
+    assert not torch.equal(G_big[:20], G_small) and rel(G_big[:20], G_small) < 1e-4 and rel(b_big[:20], b_small) < 1e-4
