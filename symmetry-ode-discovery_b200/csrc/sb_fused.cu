@@ -763,7 +763,9 @@ int launch_fused(const FusedArgs& a, void* ws, int64_t ws_bytes, cudaStream_t s,
   // 0.2831 with prefetch (variant 53; 0.3184 without), (3,3) 0.5624 -> 0.5329 without (variant 21; 0.5552 with), (2,2)
   // 0.2634 -> 0.2744 / 0.2667 (stays on 2048 x 3); a third 4096-sample stage at d = 2 changes nothing (0.2826 / 0.2599); two
   // prediction chains on the 4096-sample tiles are slower ((3,3) 0.5527, (2,3) 0.2954 with prefetch).
-  const int chosen = small_variant() ? small_variant() : ((D == 2 && P == 3) ? 53 : ((D == 3 && P == 3) ? 21 : 13));
+  // (3,2) K = 10: 0.3765 ms on 2048 x 3 = 0.97 of the HBM peak already; (2,2,exp) K = 8 (code 12): 0.3327 -> 0.3076 on 53.
+  const int chosen = small_variant() ? small_variant()
+                                     : ((D == 2 && (P == 3 || P == 12)) ? 53 : ((D == 3 && P == 3) ? 21 : 13));
   switch (chosen) {
     case 13: return launch_fused_var<D, P, LEFT, 13>(a, ws, ws_bytes, s, slot);   // 2048 x 3 ring
     case 37: return launch_fused_var<D, P, LEFT, 37>(a, ws, ws_bytes, s, slot);   // 1024 x 4 ring + next-sample prefetch

@@ -6,8 +6,9 @@ import os, sys, torch
 sys.path[:0] = [%r, %r]
 from sindy_b200 import native
 n = 10**8
-for (d, p) in ((2, 2), (2, 3), (3, 3)):
-    lib = native.Library(d, p)
+shapes = [(2, 2, 0), (2, 3, 0), (3, 3, 0)] if not os.environ.get('AB_MORE') else [(3, 2, 0), (2, 2, 1)]
+for (d, p, ex) in shapes:
+    lib = native.Library(d, p, False, bool(ex))
     g = torch.Generator(device="cuda").manual_seed(1)
     x = torch.rand(n, d, device="cuda", generator=g) * 2 - 1
     dx = torch.randn(n, d, device="cuda", generator=g)
@@ -21,7 +22,7 @@ for (d, p) in ((2, 2), (2, 3), (3, 3)):
         a.record(); native.train_step(x, dx, W, lib, 3, out=out); b.record(); torch.cuda.synchronize()
         ts.append(a.elapsed_time(b))
     ts.sort()
-    print("variant", os.environ.get("SB_FUSED_VARIANT_SMALL"), (d, p), "median %%.4f ms best %%.4f ms -> %%.0f GB/s" %% (ts[7], ts[0], 8 * d * n / ts[7] / 1e6))
+    print("variant", os.environ.get("SB_FUSED_VARIANT_SMALL"), (d, p, ex), "median %%.4f ms best %%.4f ms -> %%.0f GB/s" %% (ts[7], ts[0], 8 * d * n / ts[7] / 1e6))
     del x, dx
 ''' % (ROOT, os.path.join(ROOT, "symmetry-ode-discovery_b200"))
 for v in sys.argv[1:] or ["5", "13", "37", "45"]:
