@@ -22,7 +22,7 @@ from sindy_b200 import native, ops
 
 __all__ = [
     "symmreg_i", "symmreg_f", "symmreg_r", "symmreg_r_precomputed", "precompute_symmreg_r", "odeint", "EulerFlowMap",
-    "group_action_and_jacobian",
+    "group_action_and_jacobian", "encode_constant_component",
     "make_symmreg", "make_symmreg_pttrain", "make_symmreg_np", "make_fsymmreg", "make_fsymmreg_pttrain",
     "make_fsymmreg_np", "make_rsymmreg", "make_rsymmreg_pttrain",
 ]
@@ -106,9 +106,26 @@ def _decoder_tangent(autoencoder, z, v, require_grad):
     return _jvp_fn(require_grad)(autoencoder.decoder, z, v=v)[1]
 
 
-def _centred_latent(autoencoder, x, normalize, z_mean, fast_ok=True):
-    """z = encode(x) − centre, centre = batch mean ('in_batch') or z_mean / last BatchNorm bias ('global')."""
-    z = _encode(autoencoder, x, fast_ok)
+def encode_constant_component(autoencoder, x):
+    """Encoder output of the DATA half of x_fx = [x, f(x)] (`train.py:669-673`), (B × latent), for `symmreg_i(..., z_x=)`:
+    x does not change during a fit, the encoder is row-wise (Linear + eval-mode BatchNorm + ReLU), so its value on the x
+    rows is computed once per fit instead of in every closure — and needs no backward. Only with the tensor-core MLP
+    (None otherwise: the PyTorch module's reshapes pair the rows of a batch)."""
+    fast = _fast_ae(autoencoder, x)
+    if fast is None:
+        return None
+    with torch.no_grad():
+        return fast[0].value_rows(x)
+
+
+def _centred_latent(autoencoder, x, normalize, z_mean, fast_ok=True, z_first=None):
+    """z = encode(x) − centre, centre = batch mean ('in_batch') or z_mean / last BatchNorm bias ('global').
+    z_first: precomputed encoder output of x[:, 0] (`encode_constant_component`)."""
+    fast = _fast_ae(autoencoder, x) if (z_first is not None and fast_ok) else None
+    if fast is not None and x.dim() == 3 and x.shape[1] == 2 and z_first.shape[0] == x.shape[0]:
+        z = torch.stack([z_first, fast[0].value_rows(x[:, 1])], dim=1)
+    else:
+        z = _encode(autoencoder, x, fast_ok)
     if normalize == 'in_batch':
         z = z - z.mean(dim=0, keepdim=True)
     elif normalize == 'global':
@@ -125,12 +142,13 @@ def _act_on_latent(mat, z):
 
 
 def symmreg_i(x_fx, autoencoder, generator, f=None, dfdx=None, normalize='global', z_mean=None, relative=True,
-              require_grad=False, numpy=False):
+              require_grad=False, numpy=False, z_x=None):
     '''
     Infinitesimal (Lie-derivative) symmetry loss: for every generator v,
         mean((J_f(x)·v_x − v_fx)²) [/ mean((J_f(x)·v_x)²) if relative],
     with (v_x, v_fx) = J_decoder(z)·(v z), z = encode([x, f(x)]) − centre.
     x_fx: (batch, 2, input_dim) input and predicted output; f: map to be symmetrised (or dfdx: its Jacobian).
+    z_x (extension): `encode_constant_component(autoencoder, x_fx[:, 0])`, computed once per fit.
     '''
     if numpy:
         x_fx = torch.from_numpy(x_fx).float().to(autoencoder.device)
@@ -147,7 +165,7 @@ def symmreg_i(x_fx, autoencoder, generator, f=None, dfdx=None, normalize='global
     generator.eval()
 
     with torch.set_grad_enabled(require_grad):
-        z, _ = _centred_latent(autoencoder, x_fx, normalize, z_mean)
+        z, _ = _centred_latent(autoencoder, x_fx, normalize, z_mean, z_first=z_x)
         x = x_fx[:, 0]
         loss = 0.0
         for v in generator.get_full_basis_list():

@@ -265,6 +265,14 @@ class FrozenMLP:
 
     __call__ = value
 
+    def value_rows(self, x: torch.Tensor) -> torch.Tensor:
+        """module applied to the rows of a 2-D tensor, (rows × out) without the module's own output reshape."""
+        saved, self.out_shape = self.out_shape, None
+        try:
+            return self.value(x.reshape(-1, self.in_dim))
+        finally:
+            self.out_shape = saved
+
     def value_and_jvp(self, x: torch.Tensor, t: torch.Tensor):
         rows, trows = self._rows(x, "x"), self._rows(t, "t")
         if trows.shape[0] != rows.shape[0]:

@@ -18,7 +18,7 @@ from copy import deepcopy
 import numpy as np
 import torch
 
-from model_utils import (EulerFlowMap, group_action_and_jacobian, make_fsymmreg_pttrain, make_rsymmreg_pttrain,
+from model_utils import (EulerFlowMap, encode_constant_component, group_action_and_jacobian, make_fsymmreg_pttrain, make_rsymmreg_pttrain,
                          make_symmreg_pttrain, odeint, symmreg_r_precomputed)
 from sindy import solve_SINDy_one_step
 
@@ -165,6 +165,8 @@ def train_SIGED_lbfgs(
     group_cache = None
     if w_sym_reg > 0.0 and sym_reg_type == 'r' and not use_latent and kwargs.get('precompute_group', True):
         group_cache = group_action_and_jacobian(x, autoencoder, generator)
+    # symmreg_i encodes [x, f(x)]: the x half never changes during the fit and needs no gradient
+    z_x = encode_constant_component(autoencoder, x) if (w_sym_reg > 0.0 and sym_reg_type == 'i' and not use_latent) else None
 
     def data_loss(losses):
         if use_latent:
@@ -187,7 +189,7 @@ def train_SIGED_lbfgs(
                 # (f(x), J_f(x)·v) from one fused launch instead of a double vjp through the Euler steps
                 forward_step = EulerFlowMap(regressor, int_t, int_dt)
                 x_fx = torch.stack([x, forward_step(x)], dim=1)
-                loss_sym = symm_loss(x_fx, f=forward_step)
+                loss_sym = symm_loss(x_fx, f=forward_step, **({'z_x': z_x} if z_x is not None else {}))
             elif group_cache:
                 # g(x), J_g(x) do not depend on Ξ: formed once for the (fixed) batch, then one streaming launch per
                 # group element and closure (`model_utils.py:126-170`)

@@ -216,6 +216,11 @@ def test_symmetry_regularisers_through_the_tensor_core_chain(mlp, monkeypatch):
         li = model_utils.symmreg_i(x_fx, ae, gen, f=flow, require_grad=True)
         reg.zero_grad(); li.backward()
         out["i"] = (float(li), reg.Xi.grad.clone())
+        z_x = model_utils.encode_constant_component(ae, x)            # None when the PyTorch modules are in use
+        x_fx = torch.stack([x, flow(x)], dim=1)
+        lz = model_utils.symmreg_i(x_fx, ae, gen, f=flow, require_grad=True, z_x=z_x)
+        reg.zero_grad(); lz.backward()
+        out["z"] = (float(lz), reg.Xi.grad.clone(), z_x is not None)
         x_fx = torch.stack([x, flow(x)], dim=1)
         lf = model_utils.symmreg_f(x_fx, ae, gen, f=flow, require_grad=True)
         reg.zero_grad(); lf.backward()
@@ -239,6 +244,9 @@ def test_symmetry_regularisers_through_the_tensor_core_chain(mlp, monkeypatch):
     assert ae.__dict__.get("_sb_frozen_mlps", (None, None))[1] is not None
     monkeypatch.setenv("SINDY_B200_AE_MLP", "0")
     slow = run()
+    # the encoder output of the constant data half computed once: same loss and gradient as encoding [x, f(x)] together
+    assert fast["z"][2] and not slow["z"][2]
+    assert abs(fast["z"][0] - fast["i"][0]) <= 1e-6 * abs(fast["i"][0]) and rel(fast["z"][1], fast["i"][1]) < 1e-5
     for k in "ifrb":
         assert abs(fast[k][0] - slow[k][0]) < 1e-4 * abs(slow[k][0]), k
         assert rel(fast[k][1], slow[k][1]) < 5e-4, k

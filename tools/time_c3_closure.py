@@ -34,6 +34,9 @@ dx = torch.randn(B, 2, device=dev)
 symm = model_utils.make_symmreg_pttrain(ae, gen)
 
 
+Z_X = {"on": False, "value": None}
+
+
 def closure(fused):
     reg.zero_grad()
     loss_x = reg.mse_loss(x, dx)
@@ -43,13 +46,17 @@ def closure(fused):
         def f(q):
             return model_utils.odeint(reg, q, args['int_t'], args['int_dt'])
     x_fx = torch.stack([x, f(x)], dim=1)
-    loss = loss_x + args['w_sym_reg'] * symm(x_fx, f=f)
+    extra = {'z_x': Z_X['value']} if (Z_X['on'] and Z_X['value'] is not None) else {}
+    loss = loss_x + args['w_sym_reg'] * symm(x_fx, f=f, **extra)
     loss.backward()
     return loss
 
 
-for fused, ae_tc in ((False, False), (True, False), (True, True)):
+for fused, ae_tc, zx in ((False, False, False), (True, False, False), (True, True, False), (True, True, True)):
     os.environ["SINDY_B200_AE_MLP"] = "1" if ae_tc else "0"
+    Z_X["on"] = zx
+    if zx:
+        Z_X["value"] = model_utils.encode_constant_component(ae, x)
     for _ in range(3):
         closure(fused)
     torch.cuda.synchronize()
@@ -65,7 +72,8 @@ for fused, ae_tc in ((False, False), (True, False), (True, True)):
     tot = sum(e.device_time_total for e in ev)
     n_launch = sum(e.count for e in ev)
     what = ('fused Euler flow (EulerFlowMap)' if fused else 'closure + double vjp (reference call pattern)') + \
-        (' + autoencoder on the tensor cores (sb_mlp_gemm)' if ae_tc else '')
+        (' + autoencoder on the tensor cores (sb_mlp_gemm)' if ae_tc else '') + \
+        (' + encoder output of the data half cached per fit' if zx else '')
     lv = closure(fused)
     print(f"\n=== closure, {what}: loss {float(lv):.7f}, |grad| {float(reg.Xi.grad.norm()):.7f}, "
           f"B={B} wall {wall * 1e3:.2f} ms, GPU busy {tot / 1e3:.2f} ms in {n_launch} launches ===")
