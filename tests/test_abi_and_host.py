@@ -28,6 +28,67 @@ def test_library_exports_every_declared_symbol():
     assert lib.sb_version() >= 100
 
 
+def _header_prototypes():
+    """{name: (return type, [parameter types])} parsed from include/sindy_b200.h (comments and macros stripped)."""
+    text = open(os.path.join(ROOT, "include", "sindy_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", " ", text)
+    text = "\n".join(ln for ln in text.splitlines() if not ln.lstrip().startswith("#"))
+    protos = {}
+    for ret, name, params in re.findall(r"([A-Za-z_][A-Za-z0-9_ ]*?[\s\*]+)(sb_[a-z0-9_]+)\s*\(([^()]*)\)\s*;", text):
+        plist = [] if params.strip() in ("", "void") else [q.strip() for q in params.split(",")]
+        # drop the parameter NAME: the type is everything up to the last identifier
+        types = [re.sub(r"\s*[A-Za-z_][A-Za-z0-9_]*$", "", q).strip() for q in plist]
+        protos[name] = (" ".join(ret.split()), [" ".join(t.split()) for t in types])
+    return protos
+
+
+def _c_kind(ctype: str) -> str:
+    """Coarse ABI class of a C type as written in the header."""
+    t = ctype.replace("const ", "").replace(" const", "").strip()
+    if t.endswith("*"):
+        return "char*" if t == "char*" or t == "char *" else "ptr"
+    return {"int": "i32", "int32_t": "i32", "uint32_t": "u32", "int64_t": "i64", "unsigned long long": "u64",
+            "float": "f32", "double": "f64", "void": "void"}[t]
+
+
+def _ctypes_kind(ct) -> str:
+    if ct is None:
+        return "void"
+    if ct is ctypes.c_char_p:
+        return "char*"
+    if ct is ctypes.c_void_p or isinstance(ct, type) and issubclass(ct, ctypes._Pointer):
+        return "ptr"
+    return {ctypes.c_int: "i32", ctypes.c_int32: "i32", ctypes.c_uint32: "u32", ctypes.c_int64: "i64",
+            ctypes.c_ulonglong: "u64", ctypes.c_float: "f32", ctypes.c_double: "f64"}[ct]
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """The binding's (restype, argtypes) table against the prototypes of include/sindy_b200.h: same parameter count and,
+    per parameter, the same ABI class (pointer / int32 / uint32 / int64 / float / double) — a float passed where the
+    header says double, or a missing trailing argument, corrupts a call silently. The two structs are checked field by
+    field against their typedefs."""
+    from sindy_b200 import native
+    protos = _header_prototypes()
+    assert set(protos) == set(native.EXPORTED_SYMBOLS)
+    for name, (res, args) in native._SIGNATURES.items():
+        ret, params = protos[name]
+        assert _c_kind(ret) == _ctypes_kind(res), (name, ret, res)
+        assert len(params) == len(args), (name, params, args)
+        for i, (ct, at) in enumerate(zip(params, args)):
+            assert _c_kind(ct) == _ctypes_kind(at), (name, i, ct, at)
+    header = open(os.path.join(ROOT, "include", "sindy_b200.h")).read()
+    for struct, cls in (("sb_library", native._CLibrary), ("sb_fit_options", native._CFitOptions)):
+        body = re.search(r"typedef struct\s*\{([^{}]*)\}\s*" + struct + r"\s*;", header).group(1)
+        body = re.sub(r"/\*.*?\*/", " ", body, flags=re.S)
+        fields = [f.strip() for f in body.split(";") if f.strip()]
+        assert len(fields) == len(cls._fields_), (struct, fields)
+        for decl, (fname, ftype) in zip(fields, cls._fields_):
+            m = re.match(r"(.*?)([A-Za-z_][A-Za-z0-9_]*)$", decl)
+            assert m.group(2) == fname, (struct, decl, fname)
+            assert _c_kind(" ".join(m.group(1).split())) == _ctypes_kind(ftype), (struct, decl, ftype)
+
+
 @pytest.mark.parametrize("d,p,s,e", [(2, 2, 0, 0), (2, 3, 1, 1), (3, 5, 0, 0), (4, 3, 0, 1), (8, 2, 1, 1), (1, 5, 0, 0)])
 def test_library_size_and_exponents(d, p, s, e):
     from sindy_b200 import native
