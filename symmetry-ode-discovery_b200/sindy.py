@@ -28,7 +28,55 @@ from sindy_b200 import native, ops
 from sindy_b200.native import Library
 
 __all__ = ["SINDyRegression", "solve_SINDy_one_step", "solve_SINDy", "WSINDyWrapper", "stlsq_statistics",
-           "allreduce_statistics"]
+           "allreduce_statistics", "SINDyConst", "SINDyPoly1", "SINDyPoly2", "SINDyPoly3", "SINDySine", "SINDyExp"]
+
+
+# ---- the reference's per-block library functions (`sindy.py:7-30`) --------------------------------------------------
+# In the reference Θ is the concatenation of these six callables' outputs; here the columns are produced inside the
+# kernels and nothing in this package calls them. They exist for `from sindy import *` users: each evaluates Θ of the
+# smallest library containing its block with `sb_theta` and returns that block — the same column order and the same
+# left-to-right products (monomials bit-exact, sin / exp within 2 ulp of torch's). Values only: a tensor that carries a
+# gradient is refused instead of silently losing it (differentiate through `SINDyRegression.forward`). CUDA tensors
+# only, like everything else here.
+def _library_block(x, poly_order, sine, exp, lo, hi):
+    if not torch.is_tensor(x) or x.dim() < 1:
+        raise TypeError("expected a tensor (..., d)")
+    if torch.is_grad_enabled() and x.requires_grad:
+        raise NotImplementedError("the per-block library functions return values only; differentiate through "
+                                  "SINDyRegression.forward / ops.sindy_forward")
+    d = int(x.shape[-1])
+    theta = native.theta(x, Library(d, poly_order, sine, exp))
+    lo, hi = lo(d), hi(d)
+    return theta[..., lo:hi].contiguous()
+
+
+def _n_upto(d, n):
+    """Number of monomials of degree <= n in d variables (the polynomial block ends there)."""
+    return math.comb(d + n, n)
+
+
+def SINDyConst(x):
+    return _library_block(x, 1, False, False, lambda d: 0, lambda d: 1)
+
+
+def SINDyPoly1(x):
+    return _library_block(x, 1, False, False, lambda d: 1, lambda d: _n_upto(d, 1))
+
+
+def SINDyPoly2(x):
+    return _library_block(x, 2, False, False, lambda d: _n_upto(d, 1), lambda d: _n_upto(d, 2))
+
+
+def SINDyPoly3(x):
+    return _library_block(x, 3, False, False, lambda d: _n_upto(d, 2), lambda d: _n_upto(d, 3))
+
+
+def SINDySine(x):
+    return _library_block(x, 1, True, False, lambda d: _n_upto(d, 1), lambda d: _n_upto(d, 1) + d)
+
+
+def SINDyExp(x):
+    return _library_block(x, 1, False, True, lambda d: _n_upto(d, 1), lambda d: _n_upto(d, 1) + d)
 
 
 def _poly_index_tuples(dim: int, order: int):

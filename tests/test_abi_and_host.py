@@ -112,6 +112,19 @@ def test_unsupported_libraries_are_rejected_loudly():
         native.forward(torch.zeros(3, 2), torch.zeros(2, 6), native.Library(2, 2))
 
 
+def test_per_block_library_functions_refuse_what_they_cannot_do():
+    """`sindy.py:7-30` helpers: values from the CUDA path only — a CPU tensor raises (no fallback), a tensor that
+    carries a gradient raises instead of losing it."""
+    import sindy
+    for fn in (sindy.SINDyConst, sindy.SINDyPoly1, sindy.SINDyPoly2, sindy.SINDyPoly3, sindy.SINDySine, sindy.SINDyExp):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            fn(torch.zeros(5, 2))
+        with pytest.raises(NotImplementedError):
+            fn(torch.zeros(5, 2, requires_grad=True))
+    with pytest.raises(TypeError):
+        sindy.SINDyPoly2(3.0)
+
+
 def test_missing_library_fails_loudly(monkeypatch):
     from sindy_b200 import native
     monkeypatch.setattr(native, "_lib", None)

@@ -1,8 +1,8 @@
 """Drop-in check: every function / method of the reference's hot-path modules — recorded from the
 unmodified reference by `oracle/gen_golden.py api` into tests/golden/api_surface.json — exists here under the same name
 with the same parameters in the same order and with the same defaults (extra trailing keyword parameters are allowed).
-Deliberately absent: the per-column helper functions of `sindy.py:7-30` (the columns are produced inside the kernels),
-`SINDyRegression.get_Theta` (SymPy helper of the constraint set-up; replaced by exponent arithmetic) and `train_lassi`
+The per-block library functions of `sindy.py:7-30` are present (values from `sb_theta`; nothing here calls them).
+Deliberately absent: `SINDyRegression.get_Theta` (SymPy helper of the constraint set-up; replaced by exponent arithmetic) and `train_lassi`
 (LaLiGAN symmetry discovery: out of scope)."""
 import importlib
 import inspect
@@ -14,10 +14,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 API = json.load(open(os.path.join(ROOT, "tests", "golden", "api_surface.json")))
 
-ABSENT = {
-    ("sindy", "SINDyConst"), ("sindy", "SINDyPoly1"), ("sindy", "SINDyPoly2"), ("sindy", "SINDyPoly3"),
-    ("sindy", "SINDySine"), ("sindy", "SINDyExp"), ("sindy", "SINDyRegression.get_Theta"), ("train", "train_lassi"),
-}
+ABSENT = {("sindy", "SINDyRegression.get_Theta"), ("train", "train_lassi")}
 
 
 def _check(ref_params, fn, where):

@@ -59,6 +59,30 @@ def test_golden_theta_forward_step(nat, golden, d, p, s, e):
     assert rel(grad, g[t + "_grad"]) < 1e-5
 
 
+@pytest.mark.parametrize("t,d", [("d3p3s1e1", 3), ("d1p3s1e1", 1)])
+def test_golden_per_block_library_functions(nat, golden, t, d):
+    """`sindy.py:7-30`: the six per-block functions whose outputs the reference concatenates into Θ. The golden Θ of the
+    (d, 3, sine, exp) library IS that concatenation: const | poly1 | poly2 | poly3 | sin | exp."""
+    import sindy
+    g = golden("model")
+    x, th = dev(g[t + "_x"]), g[t + "_theta"]
+    n1, n2, n3 = O.term_count(d, 1), O.term_count(d, 2), O.term_count(d, 3)
+    blocks = [(sindy.SINDyConst, 0, 1), (sindy.SINDyPoly1, 1, n1), (sindy.SINDyPoly2, n1, n2), (sindy.SINDyPoly3, n2, n3)]
+    for fn, lo, hi in blocks:
+        out = fn(x)
+        assert out.shape == (x.shape[0], hi - lo) and out.is_contiguous()
+        assert np.array_equal(out.cpu().numpy(), th[:, lo:hi]), fn.__name__           # bit-exact monomials
+    np.testing.assert_allclose(sindy.SINDySine(x).cpu().numpy(), th[:, n3:n3 + d], rtol=5e-7, atol=1e-7)
+    np.testing.assert_allclose(sindy.SINDyExp(x).cpu().numpy(), th[:, n3 + d:n3 + 2 * d], rtol=5e-7, atol=1e-7)
+    x3 = x[:24].reshape(4, 6, d)                                                      # leading batch structure is kept
+    assert sindy.SINDyPoly2(x3).shape == (4, 6, n2 - n1)
+    assert torch.equal(sindy.SINDyPoly2(x3).reshape(24, -1), sindy.SINDyPoly2(x[:24]))
+    with pytest.raises(NotImplementedError):                                          # never a silently dropped gradient
+        sindy.SINDyPoly2(x.clone().requires_grad_(True))
+    with pytest.raises(RuntimeError):                                                 # no CPU fallback
+        sindy.SINDyPoly1(x.cpu())
+
+
 @pytest.mark.parametrize("d,p,s,e", LIBS + EXT_LIBS)
 @pytest.mark.parametrize("n", [1, 3, 1000, 4099])
 def test_train_step_all_sections_vs_oracle(nat, d, p, s, e, n):
