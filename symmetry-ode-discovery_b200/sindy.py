@@ -222,6 +222,15 @@ class SINDyRegression(nn.Module):
     def get_M_list(self):
         return [_lie_derivative_matrix(self.latent_dim, self.poly_order, Li) for Li in self.L_list]
 
+    def get_Theta(self):
+        """The polynomial library as a SymPy column matrix in the symbols z0..z{d-1} (reference `sindy.py:147-166`, where
+        it feeds `get_M_list`; here M comes from exponent arithmetic and this method only serves callers that want the
+        symbolic library — any poly_order, same column order as the kernels)."""
+        import sympy as sp
+        z = [sp.Symbol(f"z{i}") for i in range(self.latent_dim)]
+        return sp.Matrix([sp.Mul(*[z[i] for i in idx]) if idx else sp.Integer(1)
+                          for idx in _poly_index_tuples(self.latent_dim, self.poly_order)])
+
     def get_Q(self):
         """Null-space basis of the stacked constraint matrices (reference `sindy.py:85-115`)."""
         blocks = []

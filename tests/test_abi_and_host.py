@@ -168,6 +168,25 @@ def test_constraint_basis_matches_reference(golden):
     np.testing.assert_allclose(Qr @ Qr.T, Qo @ Qo.T, atol=1e-4)
 
 
+def test_symbolic_library_and_its_lie_derivative_matrix():
+    """`get_Theta` (reference `sindy.py:147-166`): the SURVEY §8a known answer Θ(2,3,5), and the reference's own route to
+    M — J_Θ(z)·L·z expanded in Θ with SymPy (`sindy.py:123-144`) — against the exponent arithmetic used here."""
+    import sympy as sp
+    import sindy
+    reg = sindy.SINDyRegression(3, 3, False, False, threshold=0.05, device="cpu")
+    Theta = reg.get_Theta()
+    z = sp.symbols("z0 z1 z2")
+    vals = [int(v) for v in Theta.subs(dict(zip(z, (2, 3, 5))))]
+    assert vals == [1, 2, 3, 5, 4, 6, 10, 9, 15, 25, 8, 12, 20, 18, 30, 50, 27, 45, 75, 125]
+    L = torch.tensor([[0.0, 1.0, 0.5], [-1.0, 0.0, 2.0], [-0.5, -2.0, 0.25]])
+    M = sindy._lie_derivative_matrix(3, 3, L).double().numpy()
+    lhs = Theta.jacobian(sp.Matrix(z)) * sp.Matrix(L.tolist()) * sp.Matrix(z)
+    rhs = sp.Matrix(M.tolist()) * Theta
+    assert all(sp.expand(a - b).xreplace({n: round(n, 9) for n in sp.expand(a - b).atoms(sp.Float)}) == 0
+               for a, b in zip(lhs, rhs))
+    assert sindy.SINDyRegression(2, 5, False, False, threshold=0.05, device="cpu").get_Theta().shape == (21, 1)
+
+
 def test_threshold_and_printer(golden, capsys):
     import sindy
     reg = sindy.SINDyRegression(2, 1, False, False, threshold=0.05, device="cpu", constrain_constant=True)

@@ -2,8 +2,8 @@
 unmodified reference by `oracle/gen_golden.py api` into tests/golden/api_surface.json — exists here under the same name
 with the same parameters in the same order and with the same defaults (extra trailing keyword parameters are allowed).
 The per-block library functions of `sindy.py:7-30` are present (values from `sb_theta`; nothing here calls them).
-Deliberately absent: `SINDyRegression.get_Theta` (SymPy helper of the constraint set-up; replaced by exponent arithmetic) and `train_lassi`
-(LaLiGAN symmetry discovery: out of scope)."""
+Deliberately absent from the fixture check: `train_lassi` (LaLiGAN symmetry discovery: out of scope; re-exported
+from the reference when a checkout is importable)."""
 import importlib
 import inspect
 import json
@@ -14,7 +14,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 API = json.load(open(os.path.join(ROOT, "tests", "golden", "api_surface.json")))
 
-ABSENT = {("sindy", "SINDyRegression.get_Theta"), ("train", "train_lassi")}
+ABSENT = {("train", "train_lassi")}
 
 
 def _check(ref_params, fn, where):
