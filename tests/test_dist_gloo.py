@@ -127,3 +127,27 @@ def test_single_process_step_matches_formula():
     loss, grad = mse_from_sums(packed, lib, w)
     assert abs(float(loss) - 1.0 / 100.0) < 1e-15
     assert torch.allclose(grad.double(), packed[2:].view(2, 6) * (2.0 / 100.0))
+
+
+def test_reference_arm_under_torchrun_prints_one_line_from_rank_zero():
+    """`bench.py --impl reference` launched the way the driver launches it for N > 1: rank 0 alone runs the reference's
+    CPU path and prints ONE JSON line (impl, cpu_baseline, e2e with zero copy bytes), the other rank exits 0 silently.
+    Needs the mirror of the reference (baseline/_ref, written by build()); no GPU involved."""
+    import json
+    import subprocess
+    if not os.path.isfile(os.path.join(ROOT, "baseline", "_ref", "sindy.py")):
+        pytest.skip("no reference mirror (baseline/_ref)")
+    port = 29600 + (os.getpid() % 300)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
+           "--steps", "1", "--warmup", "1", "--cpu-samples", "20000"]
+    env = dict(os.environ, OMP_NUM_THREADS="4")
+    out = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, out.stdout
+    rec = json.loads(lines[0])
+    assert rec["impl"] == "reference" and rec["n_gpus"] == 2 and rec["steps"] == 1 and rec["higher_is_better"] is True
+    assert rec["unit"] == "samples/s" and rec["value"] > 0
+    assert rec["cpu_baseline"]["kind"] == "reference" and rec["cpu_baseline"]["value"] == rec["value"]
+    assert rec["e2e"]["value"] == rec["value"] and rec["e2e"]["h2d_bytes_per_step"] == 0 == rec["e2e"]["d2h_bytes_per_step"]
